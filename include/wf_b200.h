@@ -1,0 +1,234 @@
+/*
+ * wf_b200.h -- C ABI of libwf_b200.so, the B200 (sm_100a) implementation of the hot path of
+ * cansdev/wireframe-3d-prediction: PointCloudToWireframe forward/backward, WireframeLoss and the
+ * Hungarian matchers.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; its boundary is
+ * the Python module API.  The entry points below are what a ctypes binding for that path binds:
+ * each one names the reference lines it replaces (paths relative to the reference repo).  The
+ * host-side mirror of the reference classes (wireframe-3d-prediction_b200/models, /losses) calls
+ * ONLY these functions for compute; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory unless the name ends in _host;
+ *   - row-major, innermost dimension contiguous, explicit leading dimensions where given;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or freed;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     keeps no mutable global state beyond one-time function-attribute setup;
+ *   - return 0 on success; otherwise a WF_E* code and wf_last_error() (thread-local) explains;
+ *   - no C++ exception crosses the boundary.
+ */
+#ifndef WF_B200_H
+#define WF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* wf_stream_t;
+
+enum { WF_OK = 0, WF_EINVAL = 1, WF_ECUDA = 2, WF_EUNSUPPORTED = 3, WF_ETOOBIG = 4 };
+enum { WF_F32 = 0, WF_BF16 = 1 };
+enum { WF_ACT_NONE = 0, WF_ACT_RELU = 1, WF_ACT_GELU = 2 };
+/* per-problem LSAP status, mirrors scipy's errors (losses/WireframeLoss.py:236 raises them) */
+enum { WF_LSAP_OK = 0, WF_LSAP_INFEASIBLE = 1, WF_LSAP_INVALID = 2 };
+
+int wf_version(void);
+const char* wf_last_error(void);
+/* sm count and compute capability of the current device */
+int wf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Matching
+ * ---------------------------------------------------------------------------------------- */
+
+/* losses/WireframeLoss.py:129-244 (_hungarian_matching, the live `final_cost_matrix`):
+ * per sample build the V x V cost (L1 cdist + |e-1| for the first counts[b] columns, e for the
+ * dummy columns) in shared memory and solve it with the Crouse/Jonker-Volgenant shortest
+ * augmenting path in fp64 -- one warp per sample, no host round trip.
+ * col_of_row[b*V+i] = assigned column of prediction i (columns >= counts[b] are dummies).
+ * status[b] = WF_LSAP_*; counts[b] > V gives WF_LSAP_INFEASIBLE (the reference appends inf rows
+ * and scipy raises).  cost_dump (optional, B*V*V floats) receives the matrices. */
+int wf_loss_match(const float* pred_v, const float* pred_e, const float* tgt_v,
+                  const int64_t* counts, int B, int V, int Vt, int32_t* col_of_row,
+                  int32_t* status, float* cost_dump, wf_stream_t stream);
+
+/* scipy.optimize.linear_sum_assignment on B independent float32 matrices
+ * (models/WireframeHungarianMatcher.py:70-71, models/HungarianMatcher.py:126-127).
+ * Matrix b is nr[b] x nc[b], stored at cost + b*batch_stride with leading dimension ld.
+ * col_of_row[b*max_nr+i] = column assigned to row i, or -1 (rows > cols leaves rows free).
+ * Identical index choice to scipy, ties included. */
+int wf_lsap_batched(const float* cost, int64_t batch_stride, int ld, const int32_t* nr,
+                    const int32_t* nc, int B, int max_nr, int max_nc, int32_t* col_of_row,
+                    int32_t* status, wf_stream_t stream);
+
+/* models/WireframeHungarianMatcher.py:52-67: C = wv*cdist_L1(pred, tgt) + we*|e_pred - e_tgt|.
+ * Targets are concatenated (tgt_off[B+1] prefix offsets); only the block-diagonal part the
+ * reference keeps after `C.split(sizes,-1)` is produced: cost[b] is V x (tgt_off[b+1]-tgt_off[b])
+ * at cost + b*V*ld. */
+int wf_wireframe_matcher_cost(const float* pred_v, const float* pred_e, const float* tgt_v,
+                              const float* tgt_e, const int32_t* tgt_off, int B, int V, float wv,
+                              float we, float* cost, int ld, wf_stream_t stream);
+
+/* models/HungarianMatcher.py:101-123: -softmax(logits)[label]*wc + L1(boxes)*wb - GIoU*wg. */
+int wf_detr_matcher_cost(const float* logits, const float* boxes, const int64_t* tgt_labels,
+                         const float* tgt_boxes, const int32_t* tgt_off, int B, int Q, int K,
+                         float wc, float wb, float wg, float* cost, int ld, wf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense row-MLP primitives, fp32 (heads: SURVEY K6-K10, K14; and the fp32 parity mode of K2-K4)
+ * ---------------------------------------------------------------------------------------- */
+
+/* C = alpha*op(A)*op(B) + beta*C (+ bias[n] broadcast over rows).  op(A) is M x K, op(B) is K x N.
+ * nn.Linear forward is (transA=0, transB=1); dX is (0,0); dW is (1,0) with beta=1 to accumulate. */
+int wf_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+                wf_stream_t stream);
+
+/* out = dropout(act(LayerNorm(z))) + residual  -- one fused pass per row.
+ * models/PointNetEncoder.py:37-40,58-63; models/VertexPredictor.py:28-54,110,114;
+ * models/EdgePredictor.py:31-38,57-66.  gamma==NULL skips the normalisation (pure activation,
+ * EdgePredictor.py:65-66).  z/out dtype WF_F32 or WF_BF16.  If stats_in != 0, mean/rstd are
+ * inputs (already reduced by the tensor-core epilogue), else they are outputs (may be NULL).
+ * keep (optional, M*C bytes) is a dropout keep-mask applied after the activation with keep_scale. */
+int wf_ln_act_fwd(const void* z, int z_dtype, const float* gamma, const float* beta, int act,
+                  const void* residual, const uint8_t* keep, float keep_scale, void* out,
+                  int out_dtype, float* mean, float* rstd, int stats_in, int M, int C, float eps,
+                  wf_stream_t stream);
+
+/* Backward of the above w.r.t. z, gamma, beta.  dgamma/dbeta/dcolsum (each C floats, may be NULL)
+ * are ACCUMULATED into (caller zeroes); dcolsum receives sum_m dz[m,:] = the bias gradient of the
+ * Linear that produced z. */
+int wf_ln_act_bwd(const void* dout, int dout_dtype, const void* z, int z_dtype, const float* gamma,
+                  const float* beta, const float* mean, const float* rstd, int act,
+                  const uint8_t* keep, float keep_scale, void* dz, int dz_dtype, float* dgamma,
+                  float* dbeta, float* dcolsum, int M, int C, wf_stream_t stream);
+
+/* column sums: out[c] += sum_m x[m,c]  (bias gradients of Linears without a LayerNorm behind) */
+int wf_colsum(const void* x, int dtype, int M, int C, int ld, float* out, wf_stream_t stream);
+
+/* models/VertexPredictor.py:117-127: split (B, 4V) logits into coords (B,V,3), sigmoid(existence)
+ * (B,V) and the >0.5 count (B,) int64.  Backward: d_vf = [d_coords, d_prob * p(1-p)]. */
+int wf_vertex_split_fwd(const float* vf, int B, int V, float* coords, float* prob, int64_t* count,
+                        wf_stream_t stream);
+int wf_vertex_split_bwd(const float* d_coords, const float* d_prob, const float* prob, int B, int V,
+                        float* d_vf, wf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Encoder
+ * ---------------------------------------------------------------------------------------- */
+
+/* models/PointNetEncoder.py:85-86: mask[m] = sum|x[m,:]| > 1e-9, valid[b] = max(1, #mask). */
+int wf_point_mask(const float* x, int B, int N, int D, uint8_t* mask, float* valid,
+                  wf_stream_t stream);
+
+/* First encoder layer, fused Linear(D->C)+LayerNorm+ReLU, fp32 math (intensity is un-normalised,
+ * SURVEY D6), memory-bound: models/PointNetEncoder.py:37-40 (i=0).  h dtype WF_F32 or WF_BF16. */
+int wf_enc_l1_fwd(const float* x, const float* W, const float* b, const float* gamma,
+                  const float* beta, void* h, int h_dtype, int M, int D, int C, float eps,
+                  wf_stream_t stream);
+/* Backward: recomputes the layer from x (no saved activations); accumulates dW[C,D], db, dgamma,
+ * dbeta (caller zeroes); dx optional (M*D floats, written). */
+int wf_enc_l1_bwd(const float* x, const float* W, const float* b, const float* gamma,
+                  const float* beta, const void* dh, int dh_dtype, float* dW, float* db,
+                  float* dgamma, float* dbeta, float* dx, int M, int D, int C, float eps,
+                  wf_stream_t stream);
+
+/* Wide per-point layers on the 5th-gen tensor cores (tcgen05.mma, TMA-fed, TMEM accumulators):
+ *   D[M,N] (+)= A * B^T (+ bias)
+ * a_kmajor/b_kmajor = 1: operand stored [rows, K] with K contiguous (activations, weights);
+ * = 0: operand stored [K, rows] with rows contiguous (the dW = dZ^T * H reduction over points).
+ * out_dtype WF_BF16 (store) or WF_F32 (store, or atomic accumulate when accumulate != 0, used with
+ * split_k > 1).  rowstats (optional, M*2 floats, ACCUMULATED): per-row sum and sum of squares of
+ * the fp32 result incl. bias -- the LayerNorm statistics of models/PointNetEncoder.py:38.
+ * Constraints: K % 8 == 0, lda/ldb % 8 == 0 (16-byte TMA strides), pointers 16-byte aligned. */
+int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M,
+                 int N, int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate,
+                 int split_k, float* rowstats, wf_stream_t stream);
+
+/* (sum, sumsq) -> (mean, rstd) per row */
+int wf_stats_finalize(const float* rowstats, int M, int C, float eps, float* mean, float* rstd,
+                      wf_stream_t stream);
+
+/* fp32 -> bf16 cast, optionally transposed ([R,C] -> [C,R]) -- weight staging for the GEMMs */
+int wf_cast_bf16(const float* src, int R, int C, void* dst, int transpose, wf_stream_t stream);
+
+/* models/PointNetEncoder.py:103-111 + models/VertexPredictor.py:86-87: the four reductions of the
+ * (B,N,C) point-feature tensor -- masked max(+first argmax)/mean and unmasked max(+argmax)/mean. */
+int wf_pool_fwd(const float* pf, const uint8_t* mask, const float* valid, int B, int N, int C,
+                float* max_m, int32_t* arg_m, float* avg_m, float* max_u, int32_t* arg_u,
+                float* mean_u, wf_stream_t stream);
+/* Backward: d_pf[b,n,c] = mask*g_avg/valid + g_mean/N + [n==arg_m]*g_max_m*finite + [n==arg_u]*g_max_u */
+int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u,
+                const float* g_mean_u, const int32_t* arg_m, const int32_t* arg_u,
+                const uint8_t* mask, const float* valid, int B, int N, int C, void* d_pf,
+                int d_dtype, wf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Edge head: ragged batch, vertices of all samples concatenated,
+ * v_off[B+1] vertex prefix offsets, e_off[B+1] edge prefix offsets (int64), T = v_off[B]
+ * (the host mirror knows T: counts are an input in training and one D2H read in inference).
+ * ---------------------------------------------------------------------------------------- */
+
+/* predicted_vertices[b, :count_b] -> packed [T,3] (models/PointCloudToWireframe.py:81,91) */
+int wf_gather_prefix(const float* verts, int B, int V, const int32_t* v_off, int T, float* packed,
+                     wf_stream_t stream);
+int wf_scatter_prefix_add(const float* d_packed, int B, int V, const int32_t* v_off, int T,
+                          float* d_verts, wf_stream_t stream);
+
+/* 8-head self-attention core of nn.MultiheadAttention (models/EdgePredictor.py:109-111):
+ * qkv [T,3*E] (in_proj output), one CTA per (sample, head); out [T,E] is the concatenated heads
+ * (input of out_proj).  probs (optional) saves softmax for the backward at p_off[b] + h*c*c.
+ * keep (optional) is the attention-dropout keep mask in the same layout. */
+int wf_attn_fwd(const float* qkv, const int32_t* v_off, const int64_t* p_off, int B, int heads,
+                int head_dim, int max_c, float* out, float* probs, const uint8_t* keep,
+                float keep_scale, wf_stream_t stream);
+int wf_attn_bwd(const float* d_out, const float* qkv, const float* probs, const int32_t* v_off,
+                const int64_t* p_off, int B, int heads, int head_dim, int max_c, float* d_qkv,
+                const uint8_t* keep, float keep_scale, wf_stream_t stream);
+
+/* All-pairs first edge layer without materialising the (E,1031) concat
+ * (models/EdgePredictor.py:117-134 + edge_mlp.0): z1[e] = P[i] + Q[j] + wd*|v_i - v_j|_2 + b,
+ * pairs (i<j) in the reference's row-major order.  P,Q are the per-vertex halves of the layer. */
+int wf_edge_pair_fwd(const float* P, const float* Q, const float* verts, const float* wd,
+                     const float* bias, const int32_t* v_off, const int64_t* e_off, int B, int T,
+                     int C, float* z1, float* dist, wf_stream_t stream);
+/* dP,dQ [T,C] written; d_verts [T,3] and d_wd[C] accumulated (caller zeroes).  The bias gradient
+ * is the column sum of dP (every pair contributes once to exactly one dP row): use wf_colsum. */
+int wf_edge_pair_bwd(const float* dz1, const float* dist, const float* verts, const float* wd,
+                     const int32_t* v_off, const int64_t* e_off, int B, int T, int C, float* dP,
+                     float* dQ, float* d_verts, float* d_wd, wf_stream_t stream);
+
+/* edge_mlp.10 + sigmoid + zero-padding to (B, max_e): models/EdgePredictor.py:137-138,
+ * models/PointCloudToWireframe.py:103-112. */
+int wf_edge_out_fwd(const float* h, const float* w, const float* bias, const int64_t* e_off, int B,
+                    int K, int max_e, float* probs, wf_stream_t stream);
+int wf_edge_out_bwd(const float* d_probs, const float* probs, const float* h, const float* w,
+                    const int64_t* e_off, int B, int K, int max_e, float* dh, float* dw, float* db,
+                    wf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss: losses/WireframeLoss.py:38-104,248-283
+ * ---------------------------------------------------------------------------------------- */
+
+/* out[0..3] = total, vertex (matched SmoothL1), existence BCE, edge BCE; out[4] = match count;
+ * out must hold wf_loss_out_floats() floats (per-CTA partial sums follow, summed in fixed order).
+ * col_of_row is wf_loss_match's output.  min_e = min(Ep, El) columns enter the edge term. */
+int wf_loss_out_floats(void);
+int wf_loss_fwd(const float* pred_v, const float* pred_e, const float* edge_p, const float* tgt_v,
+                const float* tgt_e, const float* edge_l, const int32_t* col_of_row,
+                const int64_t* counts, int B, int V, int Vt, int Ep, int El, float w_vertex,
+                float w_edge, float w_exist, float* out, wf_stream_t stream);
+/* g_out[4] (device): upstream gradients of (total, vertex, existence, edge). */
+int wf_loss_bwd(const float* g_out, const float* pred_v, const float* pred_e, const float* edge_p,
+                const float* tgt_v, const float* tgt_e, const float* edge_l,
+                const int32_t* col_of_row, const int64_t* counts, const float* fwd_out, int B, int V,
+                int Vt, int Ep, int El, float w_vertex, float w_edge, float w_exist, float* d_pred_v,
+                float* d_pred_e, float* d_edge_p, wf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WF_B200_H */

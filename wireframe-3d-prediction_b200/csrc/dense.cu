@@ -1,0 +1,362 @@
+// fp32 row-MLP primitives: strided SIMT GEMM, fused LayerNorm+activation(+dropout)(+residual)
+// forward/backward, column sums, vertex-head split.  These carry the small-M heads
+// (feature_fusion, VertexPredictor, EdgePredictor) and the fp32 parity mode of the encoder;
+// the wide encoder layers in production precision run on gemm_tc.cu instead.
+#include "wf_common.cuh"
+
+namespace wf {
+namespace dense {
+
+// ------------------------------------------------------------------------------------------
+// C = alpha * op(A) * op(B) + beta * C + bias      64x64 CTA tile, 16-deep k-slab, 4x4 per thread
+// ------------------------------------------------------------------------------------------
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc,
+                const float* __restrict__ bias) {
+    __shared__ float As[TK][TM + 4];
+    __shared__ float Bs[TK][TN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, each 4 x 4 outputs
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += TK) {
+        // ---- stage A (op(A) is M x K)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int m, k;
+            if (!TA) { k = tid & 15; m = (tid >> 4) + 16 * i; }      // k contiguous in memory
+            else     { m = tid & 63; k = (tid >> 6) + 4 * i; }       // m contiguous in memory
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+        }
+        // ---- stage B (op(B) is K x N)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int n, k;
+            if (!TB) { n = tid & 63; k = (tid >> 6) + 4 * i; }       // n contiguous
+            else     { k = tid & 15; n = (tid >> 4) + 16 * i; }      // k contiguous
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = alpha * acc[i][j];
+            if (bias) v += bias[gn];
+            float* dst = C + (size_t)gm * ldc + gn;
+            if (beta != 0.f) v += beta * (*dst);
+            *dst = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm + activation forward: one warp per row
+// ------------------------------------------------------------------------------------------
+template <int ZDT, int ODT>
+__global__ void __launch_bounds__(256)
+ln_act_fwd_kernel(const void* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                  const void* __restrict__ residual, const uint8_t* __restrict__ keep, float keep_scale,
+                  void* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, int stats_in, int M, int C,
+                  float eps) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const size_t base = (size_t)row * C;
+    float mu = 0.f, rs = 1.f;
+    if (gamma != nullptr) {
+        if (stats_in) { mu = mean[row]; rs = rstd[row]; }
+        else {
+            float s = 0.f;
+            for (int c = lane; c < C; c += 32) s += elem<ZDT>::ld(z, base + c);
+            mu = warp_sum(s) / (float)C;
+            float v = 0.f;
+            for (int c = lane; c < C; c += 32) { const float d = elem<ZDT>::ld(z, base + c) - mu; v = fmaf(d, d, v); }
+            rs = rsqrtf(warp_sum(v) / (float)C + eps);
+            if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+        }
+    }
+    for (int c = lane; c < C; c += 32) {
+        float y = elem<ZDT>::ld(z, base + c);
+        if (gamma != nullptr) y = (y - mu) * rs * gamma[c] + beta[c];
+        y = act_f(act, y);
+        if (keep != nullptr) y = keep[base + c] ? y * keep_scale : 0.f;
+        if (residual != nullptr) y += elem<ODT>::ld(residual, base + c);
+        elem<ODT>::st(out, base + c, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm + activation backward.  Block = 256 threads, ROWS rows.
+//   phase 1 (warp per row): the two row reductions  c1 = mean(g*gamma), c2 = mean(g*gamma*xhat)
+//   phase 2 (thread per column set): dz = rstd*(g*gamma - c1 - xhat*c2); per-column partial sums
+//            of g (dbeta), g*xhat (dgamma) and dz (bias grad) stay in registers, one atomic each.
+// ------------------------------------------------------------------------------------------
+constexpr int LNB_ROWS = 32;
+
+template <int GDT, int ZDT, int DDT, int CPT>
+__global__ void __launch_bounds__(256)
+ln_act_bwd_kernel(const void* __restrict__ dout, const void* __restrict__ z, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd, int act,
+                  const uint8_t* __restrict__ keep, float keep_scale, void* __restrict__ dz, float* __restrict__ dgamma,
+                  float* __restrict__ dbeta, float* __restrict__ dcolsum, int M, int C) {
+    __shared__ float c1s[LNB_ROWS], c2s[LNB_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * LNB_ROWS;
+    const bool has_ln = gamma != nullptr;
+    if (has_ln) {
+        for (int rr = warp; rr < LNB_ROWS; rr += 8) {
+            const int row = r0 + rr;
+            if (row >= M) break;
+            const size_t base = (size_t)row * C;
+            const float mu = mean[row], rs = rstd[row];
+            float a = 0.f, b = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                const float xh = (elem<ZDT>::ld(z, base + c) - mu) * rs;
+                const float y = xh * gamma[c] + beta[c];
+                float g = elem<GDT>::ld(dout, base + c);
+                if (keep != nullptr) g = keep[base + c] ? g * keep_scale : 0.f;
+                g *= act_grad_f(act, y) * gamma[c];
+                a += g; b = fmaf(g, xh, b);
+            }
+            a = warp_sum(a); b = warp_sum(b);
+            if (lane == 0) { c1s[rr] = a / (float)C; c2s[rr] = b / (float)C; }
+        }
+    }
+    __syncthreads();
+    float acc_g[CPT], acc_gx[CPT], acc_dz[CPT], gam[CPT], bet[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        acc_g[i] = acc_gx[i] = acc_dz[i] = 0.f;
+        const int c = tid + 256 * i;
+        gam[i] = (has_ln && c < C) ? gamma[c] : 1.f;
+        bet[i] = (has_ln && c < C) ? beta[c] : 0.f;
+    }
+    for (int rr = 0; rr < LNB_ROWS; ++rr) {
+        const int row = r0 + rr;
+        if (row >= M) break;
+        const size_t base = (size_t)row * C;
+        const float mu = has_ln ? mean[row] : 0.f, rs = has_ln ? rstd[row] : 1.f;
+        const float c1 = has_ln ? c1s[rr] : 0.f, c2 = has_ln ? c2s[rr] : 0.f;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int c = tid + 256 * i;
+            if (c >= C) continue;
+            const float zv = elem<ZDT>::ld(z, base + c);
+            const float xh = has_ln ? (zv - mu) * rs : zv;
+            const float y = has_ln ? xh * gam[i] + bet[i] : zv;
+            float g = elem<GDT>::ld(dout, base + c);
+            if (keep != nullptr) g = keep[base + c] ? g * keep_scale : 0.f;
+            g *= act_grad_f(act, y);
+            float d;
+            if (has_ln) {
+                d = rs * (g * gam[i] - c1 - xh * c2);
+                acc_g[i] += g; acc_gx[i] = fmaf(g, xh, acc_gx[i]);
+            } else {
+                d = g;
+            }
+            acc_dz[i] += d;
+            elem<DDT>::st(dz, base + c, d);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int c = tid + 256 * i;
+        if (c >= C) continue;
+        if (has_ln && dgamma) atomicAdd(dgamma + c, acc_gx[i]);
+        if (has_ln && dbeta) atomicAdd(dbeta + c, acc_g[i]);
+        if (dcolsum) atomicAdd(dcolsum + c, acc_dz[i]);
+    }
+}
+
+// column sums: block (32 columns x 8 row lanes), chunk of rows per block, one atomic per column
+template <int DT>
+__global__ void colsum_kernel(const void* __restrict__ x, int M, int C, int ld, float* __restrict__ out, int rows_per_block) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    if (c < C)
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) s += elem<DT>::ld(x, (size_t)r * ld + c);
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+
+__global__ void vertex_split_fwd_kernel(const float* __restrict__ vf, int B, int V, float* __restrict__ coords,
+                                        float* __restrict__ prob, long long* __restrict__ count) {
+    const int b = blockIdx.x;
+    int local = 0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const float* s = vf + ((size_t)b * V + v) * 4;
+        float* d = coords + ((size_t)b * V + v) * 3;
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+        const float p = 1.0f / (1.0f + expf(-s[3]));
+        prob[(size_t)b * V + v] = p;
+        local += p > 0.5f ? 1 : 0;
+    }
+    __shared__ int tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    atomicAdd(&tot, local);
+    __syncthreads();
+    if (threadIdx.x == 0) count[b] = tot;
+}
+
+__global__ void vertex_split_bwd_kernel(const float* __restrict__ d_coords, const float* __restrict__ d_prob,
+                                        const float* __restrict__ prob, int n, float* __restrict__ d_vf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* d = d_vf + (size_t)i * 4;
+    d[0] = d_coords ? d_coords[(size_t)i * 3 + 0] : 0.f;
+    d[1] = d_coords ? d_coords[(size_t)i * 3 + 1] : 0.f;
+    d[2] = d_coords ? d_coords[(size_t)i * 3 + 2] : 0.f;
+    const float p = prob[i];
+    d[3] = d_prob ? d_prob[i] * p * (1.0f - p) : 0.f;
+}
+
+}  // namespace dense
+}  // namespace wf
+
+extern "C" int wf_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                           int ldb, float beta, float* C, int ldc, const float* bias, wf_stream_t stream) {
+    using namespace wf;
+    using namespace wf::dense;
+    if (M <= 0 || N <= 0) return WF_OK;
+    WF_CHECK_ARG(K >= 0 && lda > 0 && ldb > 0 && ldc >= N, "wf_gemm_f32: bad dims");
+    dim3 grid(cdiv(N, TN), cdiv(M, TM));
+    cudaStream_t s = as_stream(stream);
+    if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    else gemm_f32_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_ln_act_fwd(const void* z, int z_dtype, const float* gamma, const float* beta, int act, const void* residual,
+                             const uint8_t* keep, float keep_scale, void* out, int out_dtype, float* mean, float* rstd,
+                             int stats_in, int M, int C, float eps, wf_stream_t stream) {
+    using namespace wf;
+    using namespace wf::dense;
+    if (M <= 0 || C <= 0) return WF_OK;
+    WF_CHECK_ARG(!(gamma && !beta), "wf_ln_act_fwd: gamma without beta");
+    WF_CHECK_ARG(!(stats_in && (!mean || !rstd)), "wf_ln_act_fwd: stats_in needs mean/rstd");
+    dim3 grid(cdiv(M, 8));
+    cudaStream_t s = as_stream(stream);
+#define WF_LNF(ZD, OD) ln_act_fwd_kernel<ZD, OD><<<grid, 256, 0, s>>>(z, gamma, beta, act, residual, keep, keep_scale, out, mean, rstd, stats_in, M, C, eps)
+    if (z_dtype == WF_F32 && out_dtype == WF_F32) WF_LNF(WF_F32, WF_F32);
+    else if (z_dtype == WF_BF16 && out_dtype == WF_BF16) WF_LNF(WF_BF16, WF_BF16);
+    else if (z_dtype == WF_F32 && out_dtype == WF_BF16) WF_LNF(WF_F32, WF_BF16);
+    else if (z_dtype == WF_BF16 && out_dtype == WF_F32) WF_LNF(WF_BF16, WF_F32);
+    else { set_error("wf_ln_act_fwd: bad dtypes"); return WF_EINVAL; }
+#undef WF_LNF
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+namespace wf { namespace dense {
+template <int GD, int ZD, int DD>
+static int launch_ln_bwd(const void* dout, const void* z, const float* gamma, const float* beta, const float* mean,
+                         const float* rstd, int act, const uint8_t* keep, float keep_scale, void* dz, float* dgamma,
+                         float* dbeta, float* dcolsum, int M, int C, cudaStream_t s) {
+    dim3 grid(cdiv(M, LNB_ROWS));
+#define WF_LNB(CPT) ln_act_bwd_kernel<GD, ZD, DD, CPT><<<grid, 256, 0, s>>>(dout, z, gamma, beta, mean, rstd, act, keep, keep_scale, dz, dgamma, dbeta, dcolsum, M, C)
+    if (C <= 256) WF_LNB(1);
+    else if (C <= 512) WF_LNB(2);
+    else if (C <= 1024) WF_LNB(4);
+    else if (C <= 2048) WF_LNB(8);
+    else if (C <= 4096) WF_LNB(16);
+    else { set_error("wf_ln_act_bwd: C=%d > 4096 not built", C); return WF_EUNSUPPORTED; }
+#undef WF_LNB
+    return WF_OK;
+}
+}}  // namespace wf::dense
+
+extern "C" int wf_ln_act_bwd(const void* dout, int dout_dtype, const void* z, int z_dtype, const float* gamma,
+                             const float* beta, const float* mean, const float* rstd, int act, const uint8_t* keep,
+                             float keep_scale, void* dz, int dz_dtype, float* dgamma, float* dbeta, float* dcolsum, int M,
+                             int C, wf_stream_t stream) {
+    using namespace wf;
+    using namespace wf::dense;
+    if (M <= 0 || C <= 0) return WF_OK;
+    WF_CHECK_ARG(!(gamma && (!beta || !mean || !rstd)), "wf_ln_act_bwd: LayerNorm backward needs beta, mean, rstd");
+    cudaStream_t s = as_stream(stream);
+    int rc;
+    if (dout_dtype == WF_F32 && z_dtype == WF_F32 && dz_dtype == WF_F32)
+        rc = launch_ln_bwd<WF_F32, WF_F32, WF_F32>(dout, z, gamma, beta, mean, rstd, act, keep, keep_scale, dz, dgamma, dbeta, dcolsum, M, C, s);
+    else if (dout_dtype == WF_BF16 && z_dtype == WF_BF16 && dz_dtype == WF_BF16)
+        rc = launch_ln_bwd<WF_BF16, WF_BF16, WF_BF16>(dout, z, gamma, beta, mean, rstd, act, keep, keep_scale, dz, dgamma, dbeta, dcolsum, M, C, s);
+    else { set_error("wf_ln_act_bwd: dtype combination not built"); return WF_EUNSUPPORTED; }
+    if (rc != WF_OK) return rc;
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_colsum(const void* x, int dtype, int M, int C, int ld, float* out, wf_stream_t stream) {
+    using namespace wf;
+    if (M <= 0 || C <= 0) return WF_OK;
+    const int rows_per_block = 512;
+    dim3 grid(cdiv(C, 32), cdiv(M, rows_per_block)), block(32, 8);
+    if (dtype == WF_F32) dense::colsum_kernel<WF_F32><<<grid, block, 0, as_stream(stream)>>>(x, M, C, ld, out, rows_per_block);
+    else if (dtype == WF_BF16) dense::colsum_kernel<WF_BF16><<<grid, block, 0, as_stream(stream)>>>(x, M, C, ld, out, rows_per_block);
+    else { set_error("wf_colsum: bad dtype"); return WF_EINVAL; }
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_vertex_split_fwd(const float* vf, int B, int V, float* coords, float* prob, int64_t* count, wf_stream_t stream) {
+    using namespace wf;
+    if (B <= 0 || V <= 0) return WF_OK;
+    dense::vertex_split_fwd_kernel<<<B, 128, 0, as_stream(stream)>>>(vf, B, V, coords, prob, reinterpret_cast<long long*>(count));
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_vertex_split_bwd(const float* d_coords, const float* d_prob, const float* prob, int B, int V, float* d_vf,
+                                   wf_stream_t stream) {
+    using namespace wf;
+    const int n = B * V;
+    if (n <= 0) return WF_OK;
+    dense::vertex_split_bwd_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(d_coords, d_prob, prob, n, d_vf);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}

@@ -1,0 +1,385 @@
+// Encoder-side kernels that are NOT tensor-core GEMMs: validity mask, the narrow first layer
+// (memory-bound, fp32, fused Linear+LayerNorm+ReLU), LayerNorm statistics finalisation, weight
+// staging casts, and the four pooled reductions with their backward.
+#include "wf_common.cuh"
+
+#include <math_constants.h>
+
+namespace wf {
+namespace enc {
+
+// models/PointNetEncoder.py:85-86
+__global__ void point_mask_kernel(const float* __restrict__ x, int N, int D, uint8_t* __restrict__ mask,
+                                  float* __restrict__ valid) {
+    const int b = blockIdx.x;
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float* p = x + ((size_t)b * N + n) * D;
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s += fabsf(p[d]);
+        const int m = s > 1e-9f;
+        mask[(size_t)b * N + n] = (uint8_t)m;
+        local += m;
+    }
+    atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) valid[b] = (float)max(cnt, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// layer 1: one warp per point, lane owns channel pairs (64*i + 2*lane, +1), W^T staged in smem
+// ------------------------------------------------------------------------------------------
+template <int D, int CP>
+struct L1Smem {
+    float wt[D][64 * CP];      // W transposed: [k][c]
+    float b[64 * CP], g[64 * CP], be[64 * CP];
+};
+
+template <int D, int CP>
+__device__ __forceinline__ void l1_stage(L1Smem<D, CP>& s, const float* W, const float* b, const float* g, const float* be) {
+    constexpr int C = 64 * CP;
+    for (int i = threadIdx.x; i < C * D; i += blockDim.x) { const int c = i / D, k = i - c * D; s.wt[k][c] = W[i]; }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s.b[c] = b[c]; s.g[c] = g[c]; s.be[c] = be[c]; }
+    __syncthreads();
+}
+
+// z (pre-LN) for this lane's 2*CP channels of point `row`; returns mean and rstd
+template <int D, int CP>
+__device__ __forceinline__ void l1_point(const L1Smem<D, CP>& s, const float* __restrict__ x, size_t row, int lane,
+                                         float (&xv)[D], float (&z)[2 * CP], float& mu, float& rs, float eps) {
+    constexpr int C = 64 * CP;
+#pragma unroll
+    for (int k = 0; k < D; k += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(x + row * D + k);
+        xv[k] = t.x; xv[k + 1] = t.y; xv[k + 2] = t.z; xv[k + 3] = t.w;
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < CP; ++i) {
+        const int c = 64 * i + 2 * lane;
+        float a0 = s.b[c], a1 = s.b[c + 1];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float2 w = *reinterpret_cast<const float2*>(&s.wt[k][c]);
+            a0 = fmaf(xv[k], w.x, a0); a1 = fmaf(xv[k], w.y, a1);
+        }
+        z[2 * i] = a0; z[2 * i + 1] = a1;
+        sum += a0 + a1;
+    }
+    mu = warp_sum(sum) / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * CP; ++i) { const float d = z[i] - mu; var = fmaf(d, d, var); }
+    rs = rsqrtf(warp_sum(var) / (float)C + eps);
+}
+
+template <int D, int CP, int HDT>
+__global__ void __launch_bounds__(256)
+l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+              const float* __restrict__ g, const float* __restrict__ be, void* __restrict__ h, int M, float eps) {
+    __shared__ L1Smem<D, CP> s;
+    constexpr int C = 64 * CP;
+    l1_stage<D, CP>(s, W, b, g, be);
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (size_t row = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < (size_t)M; row += (size_t)gridDim.x * wpb) {
+        float xv[D], z[2 * CP], mu, rs;
+        l1_point<D, CP>(s, x, row, lane, xv, z, mu, rs, eps);
+#pragma unroll
+        for (int i = 0; i < CP; ++i) {
+            const int c = 64 * i + 2 * lane;
+            const float y0 = fmaxf((z[2 * i] - mu) * rs * s.g[c] + s.be[c], 0.f);
+            const float y1 = fmaxf((z[2 * i + 1] - mu) * rs * s.g[c + 1] + s.be[c + 1], 0.f);
+            if (HDT == WF_BF16) {
+                reinterpret_cast<__nv_bfloat162*>(h)[(row * C + c) >> 1] = __floats2bfloat162_rn(y0, y1);
+            } else {
+                reinterpret_cast<float2*>(h)[(row * C + c) >> 1] = make_float2(y0, y1);
+            }
+        }
+    }
+}
+
+// backward: two warps share a point.  Both recompute the layer (z, LayerNorm statistics and the two
+// backward row reductions need all C channels; the arithmetic is trivial next to the 1 KB/point
+// gradient read), but each keeps register accumulators for only HALF of its channels, which is what
+// keeps dW (2*CP x D per lane otherwise) out of local memory.  Block reduce in smem, then atomics.
+template <int D, int CP, int GDT, bool WANT_DX>
+__global__ void __launch_bounds__(256)
+l1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+              const float* __restrict__ g, const float* __restrict__ be, const void* __restrict__ dh,
+              float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dg, float* __restrict__ dbe,
+              float* __restrict__ dx, int M, float eps) {
+    __shared__ L1Smem<D, CP> s;
+    constexpr int C = 64 * CP;
+    constexpr int HC = CP;                   // accumulated channels per lane (half of 2*CP)
+    l1_stage<D, CP>(s, W, b, g, be);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = warp & 1, pair = warp >> 1;
+    const int ppb = blockDim.x >> 6;         // point pairs (of warps) per block
+    float aW[HC][D], ab[HC], ag[HC], abe[HC];
+#pragma unroll
+    for (int i = 0; i < HC; ++i) {
+        ab[i] = ag[i] = abe[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) aW[i][k] = 0.f;
+    }
+    for (size_t row = (size_t)blockIdx.x * ppb + pair; row < (size_t)M; row += (size_t)gridDim.x * ppb) {
+        float xv[D], z[2 * CP], mu, rs;
+        l1_point<D, CP>(s, x, row, lane, xv, z, mu, rs, eps);
+        float gy[2 * CP];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < CP; ++i) {
+            const int c = 64 * i + 2 * lane;
+            float d0, d1;
+            if (GDT == WF_BF16) {
+                const float2 t = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(dh)[(row * C + c) >> 1]);
+                d0 = t.x; d1 = t.y;
+            } else {
+                const float2 t = reinterpret_cast<const float2*>(dh)[(row * C + c) >> 1];
+                d0 = t.x; d1 = t.y;
+            }
+            z[2 * i] = (z[2 * i] - mu) * rs; z[2 * i + 1] = (z[2 * i + 1] - mu) * rs;          // z becomes xhat
+            const float y0 = z[2 * i] * s.g[c] + s.be[c], y1 = z[2 * i + 1] * s.g[c + 1] + s.be[c + 1];
+            gy[2 * i] = y0 > 0.f ? d0 : 0.f; gy[2 * i + 1] = y1 > 0.f ? d1 : 0.f;
+            const float h0 = gy[2 * i] * s.g[c], h1 = gy[2 * i + 1] * s.g[c + 1];
+            c1 += h0 + h1; c2 = fmaf(h0, z[2 * i], fmaf(h1, z[2 * i + 1], c2));
+        }
+        c1 = warp_sum(c1) / (float)C; c2 = warp_sum(c2) / (float)C;
+        // this warp's half: register index ii <-> channel slot (half ? ii + CP : ii)
+#pragma unroll
+        for (int ii = 0; ii < HC; ++ii) {
+            const float gyv = half ? gy[ii + CP] : gy[ii];
+            const float xh = half ? z[ii + CP] : z[ii];
+            const int slot = ii + half * CP;
+            const int c = 64 * (slot >> 1) + 2 * lane + (slot & 1);
+            const float dzv = rs * (gyv * s.g[c] - c1 - xh * c2);
+            ab[ii] += dzv; ag[ii] = fmaf(gyv, xh, ag[ii]); abe[ii] += gyv;
+#pragma unroll
+            for (int k = 0; k < D; ++k) aW[ii][k] = fmaf(dzv, xv[k], aW[ii][k]);
+        }
+        if (WANT_DX && half == 0) {
+            float dxl[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) dxl[k] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2 * CP; ++i) {
+                const int c = 64 * (i >> 1) + 2 * lane + (i & 1);
+                const float dzv = rs * (gy[i] * s.g[c] - c1 - z[i] * c2);
+#pragma unroll
+                for (int k = 0; k < D; ++k) dxl[k] = fmaf(dzv, s.wt[k][c], dxl[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) { const float t = warp_sum(dxl[k]); if (lane == k) dx[row * D + k] = t; }
+        }
+    }
+    // block reduction through the (now idle) weight staging buffer, then one atomic per entry
+    __syncthreads();
+    float* red = &s.wt[0][0];                 // C*D floats
+    float* red2 = s.b;                        // 3*C floats contiguous (b, g, be)
+    for (int i = threadIdx.x; i < C * D; i += blockDim.x) red[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red2[i] = 0.f;
+    __syncthreads();
+    for (int psel = 0; psel < ppb; ++psel) {  // the two halves of a pair touch disjoint channels
+        if (pair == psel) {
+#pragma unroll
+            for (int ii = 0; ii < HC; ++ii) {
+                const int slot = ii + half * CP;
+                const int c = 64 * (slot >> 1) + 2 * lane + (slot & 1);
+#pragma unroll
+                for (int k = 0; k < D; ++k) red[c * D + k] += aW[ii][k];
+                red2[c] += ab[ii]; red2[C + c] += ag[ii]; red2[2 * C + c] += abe[ii];
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < C * D; i += blockDim.x) atomicAdd(dW + i, red[i]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(db + c, red2[c]); atomicAdd(dg + c, red2[C + c]); atomicAdd(dbe + c, red2[2 * C + c]);
+    }
+}
+
+__global__ void stats_finalize_kernel(const float* __restrict__ st, int M, float invC, float eps, float* __restrict__ mean,
+                                      float* __restrict__ rstd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float mu = st[2 * (size_t)i] * invC;
+    const float var = fmaxf(st[2 * (size_t)i + 1] * invC - mu * mu, 0.f);
+    mean[i] = mu; rstd[i] = rsqrtf(var + eps);
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void cast_bf16_t_kernel(const float* __restrict__ src, int R, int C, __nv_bfloat16* __restrict__ dst) {
+    __shared__ float t[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = blockIdx.y * 32 + j;
+        t[j][threadIdx.x] = (r < R && c < C) ? src[(size_t)r * C + c] : 0.f;
+    }
+    __syncthreads();
+    const int r2 = blockIdx.y * 32 + threadIdx.x;          // output column = source row
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c2 = blockIdx.x * 32 + j;                // output row = source column
+        if (c2 < C && r2 < R) dst[(size_t)c2 * R + r2] = __float2bfloat16_rn(t[threadIdx.x][j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pooled reductions over points: block = 32 channels x 8 point lanes
+// ------------------------------------------------------------------------------------------
+__global__ void pool_fwd_kernel(const float* __restrict__ pf, const uint8_t* __restrict__ mask,
+                                const float* __restrict__ valid, int N, int C, float* __restrict__ max_m,
+                                int* __restrict__ arg_m, float* __restrict__ avg_m, float* __restrict__ max_u,
+                                int* __restrict__ arg_u, float* __restrict__ mean_u) {
+    const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+    float mm = -CUDART_INF_F, mu_ = -CUDART_INF_F, sm_ = 0.f, su = 0.f;
+    int am = -1, au = -1;
+    if (c < C) {
+        for (int n = ty; n < N; n += 8) {
+            const float v = pf[((size_t)b * N + n) * C + c];
+            const bool ok = mask[(size_t)b * N + n] != 0;
+            su += v;
+            if (v > mu_ || au < 0) { mu_ = v; au = n; }
+            if (ok) { sm_ += v; if (v > mm || am < 0) { mm = v; am = n; } }
+        }
+    }
+    __shared__ float s_mm[8][33], s_mu[8][33], s_sm[8][33], s_su[8][33];
+    __shared__ int s_am[8][33], s_au[8][33];
+    s_mm[ty][threadIdx.x] = mm; s_mu[ty][threadIdx.x] = mu_; s_sm[ty][threadIdx.x] = sm_; s_su[ty][threadIdx.x] = su;
+    s_am[ty][threadIdx.x] = am; s_au[ty][threadIdx.x] = au;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) {
+            const float v1 = s_mm[k][threadIdx.x]; const int a1 = s_am[k][threadIdx.x];
+            if (a1 >= 0 && (am < 0 || v1 > mm || (v1 == mm && a1 < am))) { mm = v1; am = a1; }
+            const float v2 = s_mu[k][threadIdx.x]; const int a2 = s_au[k][threadIdx.x];
+            if (a2 >= 0 && (au < 0 || v2 > mu_ || (v2 == mu_ && a2 < au))) { mu_ = v2; au = a2; }
+            sm_ += s_sm[k][threadIdx.x]; su += s_su[k][threadIdx.x];
+        }
+        const size_t o = (size_t)b * C + c;
+        const bool fin = am >= 0 && isfinite(mm);          // models/PointNetEncoder.py:111
+        max_m[o] = fin ? mm : 0.f; arg_m[o] = fin ? am : -1;
+        avg_m[o] = sm_ / valid[b];
+        max_u[o] = mu_; arg_u[o] = au;
+        mean_u[o] = su / (float)N;
+    }
+}
+
+template <int DDT>
+__global__ void pool_bwd_kernel(const float* __restrict__ g_max_m, const float* __restrict__ g_avg_m,
+                                const float* __restrict__ g_max_u, const float* __restrict__ g_mean_u,
+                                const int* __restrict__ arg_m, const int* __restrict__ arg_u,
+                                const uint8_t* __restrict__ mask, const float* __restrict__ valid, int N, int C,
+                                void* __restrict__ d_pf) {
+    const int b = blockIdx.z;
+    const float invN = 1.0f / (float)N;
+    const float inv_valid = 1.0f / valid[b];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)b * C + c;
+        const float ga = g_avg_m ? g_avg_m[o] * inv_valid : 0.f;
+        const float gu = g_mean_u ? g_mean_u[o] * invN : 0.f;
+        const float gm = g_max_m ? g_max_m[o] : 0.f, gx = g_max_u ? g_max_u[o] : 0.f;
+        const int am = g_max_m ? arg_m[o] : -1, au = g_max_u ? arg_u[o] : -1;
+        for (int n = blockIdx.y; n < N; n += gridDim.y) {
+            float v = gu;
+            if (mask[(size_t)b * N + n]) v += ga;
+            if (am == n) v += gm;
+            if (au == n) v += gx;
+            elem<DDT>::st(d_pf, ((size_t)b * N + n) * C + c, v);
+        }
+    }
+}
+
+}  // namespace enc
+}  // namespace wf
+
+extern "C" int wf_point_mask(const float* x, int B, int N, int D, uint8_t* mask, float* valid, wf_stream_t stream) {
+    using namespace wf;
+    if (B <= 0) return WF_OK;
+    enc::point_mask_kernel<<<B, 256, 0, as_stream(stream)>>>(x, N, D, mask, valid);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_enc_l1_fwd(const float* x, const float* W, const float* b, const float* gamma, const float* beta, void* h,
+                             int h_dtype, int M, int D, int C, float eps, wf_stream_t stream) {
+    using namespace wf;
+    if (M <= 0) return WF_OK;
+    WF_CHECK_ARG(D == 8 && C == 512, "wf_enc_l1_fwd: built for D=8, C=512 (got D=%d C=%d); use wf_gemm_f32 + wf_ln_act_fwd", D, C);
+    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "wf_enc_l1_fwd: x must be 16-byte aligned");
+    const int grid = min(cdiv(M, 8), sm_count() * 8);
+    if (h_dtype == WF_BF16) enc::l1_fwd_kernel<8, 8, WF_BF16><<<grid, 256, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
+    else if (h_dtype == WF_F32) enc::l1_fwd_kernel<8, 8, WF_F32><<<grid, 256, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
+    else { set_error("wf_enc_l1_fwd: bad dtype"); return WF_EINVAL; }
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_enc_l1_bwd(const float* x, const float* W, const float* b, const float* gamma, const float* beta,
+                             const void* dh, int dh_dtype, float* dW, float* db, float* dgamma, float* dbeta, float* dx, int M,
+                             int D, int C, float eps, wf_stream_t stream) {
+    using namespace wf;
+    if (M <= 0) return WF_OK;
+    WF_CHECK_ARG(D == 8 && C == 512, "wf_enc_l1_bwd: built for D=8, C=512 (got D=%d C=%d)", D, C);
+    const int grid = min(cdiv(M, 4), sm_count() * 4);
+#define WF_L1B(DT, DX) enc::l1_bwd_kernel<8, 8, DT, DX><<<grid, 256, 0, as_stream(stream)>>>(x, W, b, gamma, beta, dh, dW, db, dgamma, dbeta, dx, M, eps)
+    if (dh_dtype == WF_BF16) { if (dx) WF_L1B(WF_BF16, true); else WF_L1B(WF_BF16, false); }
+    else if (dh_dtype == WF_F32) { if (dx) WF_L1B(WF_F32, true); else WF_L1B(WF_F32, false); }
+#undef WF_L1B
+    else { set_error("wf_enc_l1_bwd: bad dtype"); return WF_EINVAL; }
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_stats_finalize(const float* rowstats, int M, int C, float eps, float* mean, float* rstd, wf_stream_t stream) {
+    using namespace wf;
+    if (M <= 0) return WF_OK;
+    enc::stats_finalize_kernel<<<cdiv(M, 256), 256, 0, as_stream(stream)>>>(rowstats, M, 1.0f / (float)C, eps, mean, rstd);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_cast_bf16(const float* src, int R, int C, void* dst, int transpose, wf_stream_t stream) {
+    using namespace wf;
+    if (R <= 0 || C <= 0) return WF_OK;
+    if (!transpose) {
+        const size_t n = (size_t)R * C;
+        enc::cast_bf16_kernel<<<cdiv((long long)n, 256), 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    } else {
+        dim3 grid(cdiv(C, 32), cdiv(R, 32)), block(32, 8);
+        enc::cast_bf16_t_kernel<<<grid, block, 0, as_stream(stream)>>>(src, R, C, static_cast<__nv_bfloat16*>(dst));
+    }
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_pool_fwd(const float* pf, const uint8_t* mask, const float* valid, int B, int N, int C, float* max_m,
+                           int32_t* arg_m, float* avg_m, float* max_u, int32_t* arg_u, float* mean_u, wf_stream_t stream) {
+    using namespace wf;
+    if (B <= 0 || C <= 0) return WF_OK;
+    WF_CHECK_ARG(N > 0, "wf_pool_fwd: N must be positive");
+    dim3 grid(cdiv(C, 32), B), block(32, 8);
+    enc::pool_fwd_kernel<<<grid, block, 0, as_stream(stream)>>>(pf, mask, valid, N, C, max_m, arg_m, avg_m, max_u, arg_u, mean_u);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u, const float* g_mean_u,
+                           const int32_t* arg_m, const int32_t* arg_u, const uint8_t* mask, const float* valid, int B, int N,
+                           int C, void* d_pf, int d_dtype, wf_stream_t stream) {
+    using namespace wf;
+    if (B <= 0 || N <= 0 || C <= 0) return WF_OK;
+    WF_CHECK_ARG(B <= 65535, "wf_pool_bwd: B > 65535");
+    dim3 grid(cdiv(C, 256), N < 16384 ? N : 16384, B);
+    if (d_dtype == WF_F32) enc::pool_bwd_kernel<WF_F32><<<grid, 256, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid, N, C, d_pf);
+    else if (d_dtype == WF_BF16) enc::pool_bwd_kernel<WF_BF16><<<grid, 256, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid, N, C, d_pf);
+    else { set_error("wf_pool_bwd: bad dtype"); return WF_EINVAL; }
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}

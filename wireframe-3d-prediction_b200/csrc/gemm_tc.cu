@@ -1,0 +1,308 @@
+// wf_gemm_bf16: persistent, warp-specialised tcgen05 GEMM for the wide per-point encoder layers
+// (models/PointNetEncoder.py:37-45, i=1..3 and the final projection) and their backward.
+//
+//   D[M,N] (+)= A * B^T (+bias)      bf16 operands, fp32 accumulation in TMEM
+//
+//   CTA tile 128 x 256, K step 64 (= one 128-byte swizzle row of bf16), 4-stage TMA ring
+//   (48 KB per stage), two 256-column TMEM accumulator stages so the epilogue of tile i
+//   overlaps the MMAs of tile i+1.  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one
+//   elected lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp%4).
+//
+//   Operand layouts (both through the same 64-element-wide TMA boxes, SWIZZLE_128B):
+//     K-major  : operand stored [rows, K], K contiguous  -> descriptor LBO unused, SBO = 1024 B
+//     MN-major : operand stored [K, rows], rows contiguous (dW = dZ^T * H, reduction over
+//                points) -> one 64x64 box per 64 rows, LBO = 8192 B (next box), SBO = 1024 B
+//
+//   Epilogue (thread = accumulator row): + bias, optional per-row (sum, sumsq) for the following
+//   LayerNorm, then bf16 store, fp32 store or fp32 atomic accumulate (split-K).
+#include "wf_common.cuh"
+#include "sm100_ptx.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace wf {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = BN * BK * 2;          // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BOX_BYTES = 64 * 64 * 2;        // one MN-major box
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int TMEM_COLS = 512;
+constexpr int NTHREADS = 256;
+
+struct Params {
+    int M, N, K;
+    int tiles_m, tiles_n, split_k, kb_per_split, nkb;
+    const float* bias;
+    void* D;
+    int ldd, out_dtype, accumulate;
+    float* rowstats;
+};
+
+template <bool KMAJOR>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.tiles_m * p.tiles_n * p.split_k;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m, split = w / (p.tiles_n * p.tiles_m);
+                const int kb0 = split * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    if (KMAJOR) {
+                        ptx::tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m_blk * BM);
+                        ptx::tma_load_2d(sb, &map_b, full_bar(stage), kb * BK, n_blk * BN);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            ptx::tma_load_2d(sa + i * BOX_BYTES, &map_a, full_bar(stage), m_blk * BM + i * 64, kb * BK);
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            ptx::tma_load_2d(sb + i * BOX_BYTES, &map_b, full_bar(stage), n_blk * BN + i * 64, kb * BK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
+            constexpr uint32_t LBO = KMAJOR ? 16u : (uint32_t)BOX_BYTES;
+            constexpr uint32_t KSTEP = KMAJOR ? 32u : 2048u;     // bytes per UMMA_K=16 along K
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const int split = w / (p.tiles_n * p.tiles_m);
+                const int kb0 = split * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = ptx::smem_desc_sw128(sa + k * KSTEP, LBO, 1024u);
+                        const uint64_t db = ptx::smem_desc_sw128(sb + k * KSTEP, LBO, 1024u);
+                        ptx::mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::mma_commit(empty_bar(stage));           // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::mma_commit(tfull_bar(acc));                 // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m;
+            const int row = m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n_blk * BN + c * 32;
+                if (col0 >= p.N) break;                          // warp-uniform
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+                ptx::tmem_ld_wait();
+                float v[32];
+                const bool full = col0 + 32 <= p.N;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(r[j]);
+                    if (p.bias != nullptr && (full || col0 + j < p.N)) v[j] += __ldg(p.bias + col0 + j);
+                }
+                if (p.rowstats != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (full || col0 + j < p.N) { s1 += v[j]; s2 += v[j] * v[j]; }
+                }
+                if (row_ok) {
+                    if (p.out_dtype == WF_BF16) {
+                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                                *reinterpret_cast<uint4*>(dst + j) = pk;
+                            }
+                        } else {
+                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    } else {
+                        float* dst = static_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+                        if (p.accumulate) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (full || col0 + j < p.N) atomicAdd(dst + j, v[j]);
+                        } else if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = v[j];
+                        }
+                    }
+                }
+            }
+            if (p.rowstats != nullptr && row_ok) {
+                atomicAdd(p.rowstats + 2 * (size_t)row, s1);
+                atomicAdd(p.rowstats + 2 * (size_t)row + 1, s2);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// 2-D bf16 tensor map: inner dimension `inner` elements (contiguous), `outer` rows of stride ld elements.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return WF_ECUDA; }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
+                                       (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return WF_ECUDA; }
+    return WF_OK;
+}
+
+}  // namespace tc
+}  // namespace wf
+
+extern "C" int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N,
+                            int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k,
+                            float* rowstats, wf_stream_t stream) {
+    using namespace wf;
+    using namespace wf::tc;
+    WF_CHECK_ARG(M > 0 && N > 0 && K > 0, "wf_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+    WF_CHECK_ARG(a_kmajor == b_kmajor, "wf_gemm_bf16: mixed operand majorness is not built (a=%d b=%d)", a_kmajor, b_kmajor);
+    WF_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "wf_gemm_bf16: lda/ldb must be multiples of 8 (16-byte TMA strides)");
+    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                 "wf_gemm_bf16: operands must be 16-byte aligned");
+    WF_CHECK_ARG(out_dtype == WF_BF16 || out_dtype == WF_F32, "wf_gemm_bf16: bad out_dtype");
+    WF_CHECK_ARG(!(accumulate && out_dtype != WF_F32), "wf_gemm_bf16: accumulate needs an fp32 output");
+    WF_CHECK_ARG(out_dtype == WF_F32 ? (ldd % 4 == 0) : (ldd % 8 == 0), "wf_gemm_bf16: ldd alignment");
+    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "wf_gemm_bf16: D must be 16-byte aligned");
+    if (split_k < 1) split_k = 1;
+    WF_CHECK_ARG(split_k == 1 || accumulate, "wf_gemm_bf16: split_k > 1 needs accumulate");
+
+    CUtensorMap ma, mb;
+    int rc;
+    if (a_kmajor) {
+        WF_CHECK_ARG(K % 8 == 0, "wf_gemm_bf16: K %% 8 != 0");
+        if ((rc = make_map(&ma, A, K, M, lda, BK, BM)) != WF_OK) return rc;
+        if ((rc = make_map(&mb, B, K, N, ldb, BK, BN)) != WF_OK) return rc;
+    } else {
+        if ((rc = make_map(&ma, A, M, K, lda, 64, 64)) != WF_OK) return rc;
+        if ((rc = make_map(&mb, B, N, K, ldb, 64, 64)) != WF_OK) return rc;
+    }
+    Params p;
+    p.M = M; p.N = N; p.K = K;
+    p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
+    p.nkb = cdiv(K, BK);
+    if (split_k > p.nkb) split_k = p.nkb;
+    p.kb_per_split = cdiv(p.nkb, split_k);
+    p.split_k = cdiv(p.nkb, p.kb_per_split);
+    p.bias = bias; p.D = D; p.ldd = ldd; p.out_dtype = out_dtype; p.accumulate = accumulate; p.rowstats = rowstats;
+    const long long items = (long long)p.tiles_m * p.tiles_n * p.split_k;
+    const int grid = (int)(items < sm_count() ? items : sm_count());
+
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    });
+    WF_CUDA(attr_err);
+    if (a_kmajor)
+        gemm_bf16_kernel<true><<<grid, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(ma, mb, p);
+    else
+        gemm_bf16_kernel<false><<<grid, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(ma, mb, p);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}

@@ -1,0 +1,61 @@
+"""PointCloudToWireframe -- drop-in for the reference's models/PointCloudToWireframe.py.
+
+Same constructor, forward signature and output dict (models/PointCloudToWireframe.py:43-121).
+Differences in mechanism only: the encoder hands the pooled reductions straight to the vertex head
+(the (B,N,512) fp32 point-feature tensor is not kept), the per-sample edge-head loop and its B
+`.item()` syncs become one ragged launch sequence with a single host read of the counts."""
+import torch
+import torch.nn as nn
+
+from models.EdgePredictor import EdgePredictor, pair_list
+from models.PointNetEncoder import PointNetEncoder
+from models.VertexPredictor import VertexPredictor
+from wf_b200 import ops
+
+
+class PointCloudToWireframe(nn.Module):
+    def __init__(self, input_dim=8, max_vertices=64):
+        super(PointCloudToWireframe, self).__init__()
+        self.max_vertices = max_vertices
+        self.encoder = PointNetEncoder(input_dim=input_dim)
+        self.vertex_predictor = VertexPredictor(global_feature_dim=512, max_vertices=max_vertices)
+        self.edge_predictor = EdgePredictor(vertex_dim=3)
+        self._count_cache = None
+
+    def _host_counts(self, t):
+        """One device->host read per distinct counts tensor (train.py passes the same tensor every step)."""
+        if not torch.is_tensor(t):
+            return [int(c) for c in t]
+        key = (t.data_ptr(), t._version, tuple(t.shape), t.device)
+        if self._count_cache is not None and self._count_cache[0] == key:
+            return self._count_cache[1]
+        vals = [int(c) for c in t.tolist()]
+        self._count_cache = (key, vals)
+        return vals
+
+    def forward(self, point_cloud, target_vertex_counts=None):
+        ops._need_cuda(point_cloud)
+        max_m, avg_m, max_u, mean_u, _, _, _ = self.encoder.pooled(point_cloud)
+        global_features = self.encoder.fuse(max_m, avg_m)
+        vo = self.vertex_predictor.forward_pooled(global_features, mean_u, max_u)
+        verts, prob, dyn = vo['vertices'], vo['existence_probabilities'], vo['actual_vertex_counts']
+        batch_size = verts.shape[0]
+        if self.training and target_vertex_counts is not None:
+            counts = self._host_counts(target_vertex_counts)
+        else:
+            counts = [int(c) for c in dyn.tolist()]                 # the one sync of the inference path
+        counts = [min(int(c), self.max_vertices) for c in counts]  # reference slices [:count] of V rows
+        if any(c <= 1 for c in counts):
+            # models/EdgePredictor.py:117-119 raises for 0 or 1 vertices
+            raise IndexError("too many indices for tensor of dimension 1")
+        rg = ops.Ragged(counts, verts.device)
+        packed = ops.GatherPrefix.apply(verts, rg)
+        edge_probs = self.edge_predictor.forward_ragged(packed, rg)
+        return {
+            'vertices': verts,
+            'existence_probabilities': prob,
+            'edge_probs': edge_probs,
+            'edge_indices': [pair_list(c) for c in counts],
+            'global_features': global_features,
+            'actual_vertex_counts': dyn,
+        }

@@ -1,0 +1,644 @@
+"""torch.autograd.Function wrappers over the C ABI (include/wf_b200.h).
+
+PyTorch owns every tensor (inputs, outputs, saved activations, workspaces) and the autograd graph;
+every FLOP of the hot path is done by a kernel of libwf_b200.so.  Each Function's forward/backward
+is a short sequence of `_lib.call(...)`s on raw pointers and the current CUDA stream."""
+from __future__ import annotations
+
+import os
+from ctypes import c_void_p
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call
+
+_PRECISION = os.environ.get("WF_B200_PRECISION", "bf16").lower()
+
+
+def set_precision(p: str) -> None:
+    """'bf16': wide encoder layers on tcgen05 tensor cores (production).  'fp32': everything in the
+    fp32 SIMT kernels (parity mode: 1e-5-level agreement with the reference's fp32 path)."""
+    global _PRECISION
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = p
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+LAUNCHES = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _s():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.WfError("wf_b200 kernels run on CUDA tensors only; there is no CPU path "
+                               "(move the module and its inputs to a B200 device)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D fp32 with unit inner stride (views with a row stride are passed through via ld)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+# raw kernels (no autograd)
+# ----------------------------------------------------------------------------------------------
+def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0, bias=None):
+    A, B = _rowmajor(A), _rowmajor(B)
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    N = B.shape[0] if transB else B.shape[1]
+    kb = B.shape[1] if transB else B.shape[0]
+    if kb != K:
+        raise ValueError(f"gemm shape mismatch {tuple(A.shape)} {tuple(B.shape)} tA={transA} tB={transB}")
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+        beta = 0.0
+    call("wf_gemm_f32", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(B),
+         B.stride(0), float(beta), _p(out), out.stride(0), _p(bias), _s())
+    _count()
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    out = torch.zeros(x2.shape[1], device=x.device, dtype=torch.float32)
+    dt = BF16 if x2.dtype == torch.bfloat16 else F32
+    call("wf_colsum", _p(x2), dt, x2.shape[0], x2.shape[1], x2.stride(0), _p(out), _s())
+    _count()
+    return out
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+# ----------------------------------------------------------------------------------------------
+# Linear (+ LayerNorm + activation + dropout + residual)
+# ----------------------------------------------------------------------------------------------
+class LinearLNAct(torch.autograd.Function):
+    """out = dropout(act(LN(x W^T + b))) + residual.   gamma None -> no LayerNorm.
+    models/PointNetEncoder.py:37-40,58-65; models/VertexPredictor.py:28-61,105-117;
+    models/EdgePredictor.py:31-38,57-68."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, gamma, beta, act, residual, keep, keep_scale):
+        _need_cuda(x, W)
+        x2 = _rowmajor(x.reshape(-1, x.shape[-1]))
+        Wc = _rowmajor(W)
+        z = gemm_f32(x2, Wc, transB=True, bias=None if b is None else _f32c(b))
+        M, C = z.shape
+        plain = gamma is None and act == ACT_NONE and keep is None
+        mean = rstd = None
+        if plain and residual is None:
+            out = z
+        else:
+            out = torch.empty_like(z)
+            if gamma is not None:
+                mean = torch.empty(M, device=z.device, dtype=torch.float32)
+                rstd = torch.empty(M, device=z.device, dtype=torch.float32)
+            res = None if residual is None else _f32c(residual.reshape(M, C))
+            call("wf_ln_act_fwd", _p(z), F32, _p(gamma), _p(beta), int(act), _p(res), _p(keep), float(keep_scale),
+                 _p(out), F32, _p(mean), _p(rstd), 0, M, C, 1e-5, _s())
+            _count()
+        ctx.save_for_backward(x2, Wc, z if not plain else None, gamma, beta, mean, rstd, keep)
+        ctx.meta = (act, keep_scale, plain, b is not None, residual is not None, x.shape)
+        return out.reshape(*x.shape[:-1], C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, Wc, z, gamma, beta, mean, rstd, keep = ctx.saved_tensors
+        act, keep_scale, plain, has_b, has_res, xshape = ctx.meta
+        C = Wc.shape[0]
+        d2 = _f32c(dout.reshape(-1, C))
+        M = d2.shape[0]
+        dgamma = dbeta = db = None
+        if plain:
+            dz = d2
+            if has_b and ctx.needs_input_grad[2]:
+                db = colsum(dz)
+        else:
+            dz = torch.empty_like(d2)
+            if gamma is not None:
+                dgamma = torch.zeros(C, device=d2.device, dtype=torch.float32)
+                dbeta = torch.zeros(C, device=d2.device, dtype=torch.float32)
+            db = torch.zeros(C, device=d2.device, dtype=torch.float32) if has_b else None
+            call("wf_ln_act_bwd", _p(d2), F32, _p(z), F32, _p(gamma), _p(beta), _p(mean), _p(rstd), int(act),
+                 _p(keep), float(keep_scale), _p(dz), F32, _p(dgamma), _p(dbeta), _p(db), M, C, _s())
+            _count()
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_f32(dz, Wc).reshape(xshape)
+        if ctx.needs_input_grad[1]:
+            dW = gemm_f32(dz, x2, transA=True)
+        dres = dout if has_res else None
+        return dx, dW, db, dgamma, dbeta, None, dres, None, None
+
+
+def linear_ln_act(x, W, b=None, gamma=None, beta=None, act=ACT_NONE, residual=None, keep=None, keep_scale=1.0):
+    return LinearLNAct.apply(x, W, b, gamma, beta, act, residual, keep, keep_scale)
+
+
+class LNAct(torch.autograd.Function):
+    """out = dropout(act(LN(z)))  (no Linear in front: the all-pairs layer produces z itself)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, act, keep, keep_scale):
+        _need_cuda(z)
+        z2 = _f32c(z.reshape(-1, z.shape[-1]))
+        M, C = z2.shape
+        out = torch.empty_like(z2)
+        mean = torch.empty(M, device=z2.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=z2.device, dtype=torch.float32)
+        call("wf_ln_act_fwd", _p(z2), F32, _p(gamma), _p(beta), int(act), None, _p(keep), float(keep_scale), _p(out), F32,
+             _p(mean), _p(rstd), 0, M, C, 1e-5, _s())
+        _count()
+        ctx.save_for_backward(z2, gamma, beta, mean, rstd, keep)
+        ctx.meta = (act, keep_scale, z.shape)
+        return out.reshape(z.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        z2, gamma, beta, mean, rstd, keep = ctx.saved_tensors
+        act, keep_scale, zshape = ctx.meta
+        M, C = z2.shape
+        d2 = _f32c(dout.reshape(M, C))
+        dz = torch.empty_like(d2)
+        dgamma = torch.zeros(C, device=d2.device, dtype=torch.float32)
+        dbeta = torch.zeros(C, device=d2.device, dtype=torch.float32)
+        call("wf_ln_act_bwd", _p(d2), F32, _p(z2), F32, _p(gamma), _p(beta), _p(mean), _p(rstd), int(act), _p(keep),
+             float(keep_scale), _p(dz), F32, _p(dgamma), _p(dbeta), None, M, C, _s())
+        _count()
+        return dz.reshape(zshape), dgamma, dbeta, None, None, None
+
+
+def dropout_keep(shape, p: float, training: bool, device) -> Tuple[Optional[torch.Tensor], float]:
+    """Keep-mask for a dropout site.  The mask bits come from torch's CUDA generator (RNG state is
+    plumbing); the masking itself is fused into the consuming kernel."""
+    if not training or p <= 0.0:
+        return None, 1.0
+    keep = (torch.rand(shape, device=device) >= p).to(torch.uint8)
+    return keep, 1.0 / (1.0 - p)
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling of point features (fp32 path / public encoder API)
+# ----------------------------------------------------------------------------------------------
+def point_mask(x: torch.Tensor):
+    B, N, D = x.shape
+    mask = torch.empty(B, N, device=x.device, dtype=torch.uint8)
+    valid = torch.empty(B, device=x.device, dtype=torch.float32)
+    call("wf_point_mask", _p(x), B, N, D, _p(mask), _p(valid), _s())
+    _count()
+    return mask, valid
+
+
+class PoolPoints(torch.autograd.Function):
+    """(B,N,C) -> masked max, masked mean, unmasked max, unmasked mean.
+    models/PointNetEncoder.py:103-111, models/VertexPredictor.py:86-87."""
+
+    @staticmethod
+    def forward(ctx, pf, mask, valid):
+        _need_cuda(pf)
+        pf = _f32c(pf)
+        B, N, C = pf.shape
+        mk = lambda dt: torch.empty(B, C, device=pf.device, dtype=dt)
+        max_m, avg_m, max_u, mean_u = mk(torch.float32), mk(torch.float32), mk(torch.float32), mk(torch.float32)
+        arg_m, arg_u = mk(torch.int32), mk(torch.int32)
+        call("wf_pool_fwd", _p(pf), _p(mask), _p(valid), B, N, C, _p(max_m), _p(arg_m), _p(avg_m), _p(max_u),
+             _p(arg_u), _p(mean_u), _s())
+        _count()
+        ctx.save_for_backward(arg_m, arg_u, mask, valid)
+        ctx.shape = (B, N, C)
+        ctx.mark_non_differentiable(arg_m, arg_u)
+        return max_m, avg_m, max_u, mean_u, arg_m, arg_u
+
+    @staticmethod
+    def backward(ctx, g_max_m, g_avg_m, g_max_u, g_mean_u, _a, _b):
+        arg_m, arg_u, mask, valid = ctx.saved_tensors
+        B, N, C = ctx.shape
+        d_pf = torch.empty(B, N, C, device=mask.device, dtype=torch.float32)
+        f = lambda g: None if g is None else _f32c(g)
+        call("wf_pool_bwd", _p(f(g_max_m)), _p(f(g_avg_m)), _p(f(g_max_u)), _p(f(g_mean_u)), _p(arg_m), _p(arg_u),
+             _p(mask), _p(valid), B, N, C, _p(d_pf), F32, _s())
+        _count()
+        return d_pf, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# encoder per-point MLP on tensor cores (bf16 operands, fp32 accumulate) fused with the pools
+# ----------------------------------------------------------------------------------------------
+def gemm_bf16(A, B, *, M, N, K, kmajor=True, bias=None, out, accumulate=False, split_k=1, rowstats=None):
+    lda = A.stride(0)
+    ldb = B.stride(0)
+    call("wf_gemm_bf16", _p(A), lda, int(kmajor), _p(B), ldb, int(kmajor), M, N, K, _p(bias), _p(out), out.stride(0),
+         _dt(out), int(accumulate), int(split_k), _p(rowstats), _s())
+    _count()
+    return out
+
+
+def cast_bf16(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    w = _f32c(w)
+    R, C = w.shape
+    out = torch.empty((C, R) if transpose else (R, C), device=w.device, dtype=torch.bfloat16)
+    call("wf_cast_bf16", _p(w), R, C, _p(out), int(transpose), _s())
+    _count()
+    return out
+
+
+def _sm_count() -> int:
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+class EncoderPointMLP_TC(torch.autograd.Function):
+    """x (B,N,8) -> the four pooled reductions of the (B,N,512) point features, without keeping the
+    fp32 point-feature tensor.  models/PointNetEncoder.py:85-111 + models/VertexPredictor.py:86-87.
+
+    Layer 1 (K=8) runs in fp32 SIMT (un-normalised intensity); layers 2..5 are
+    wf_gemm_bf16 (tcgen05).  LayerNorm statistics come out of the GEMM epilogue (fp32 accumulators).
+    Saved for backward: bf16 pre-LN z2..z4 and post-ReLU h1..h4 (17.4 KB/point), row statistics,
+    argmax indices."""
+
+    @staticmethod
+    def forward(ctx, x, want_pf, *params):
+        (W1, b1, g1, be1, W2, b2, g2, be2, W3, b3, g3, be3, W4, b4, g4, be4, W5, b5) = params
+        _need_cuda(x, W1)
+        x = _f32c(x)
+        B, N, D = x.shape
+        M = B * N
+        dev = x.device
+        mask, valid = point_mask(x)
+        h = torch.empty(M, W1.shape[0], device=dev, dtype=torch.bfloat16)
+        call("wf_enc_l1_fwd", _p(x), _p(_f32c(W1)), _p(b1), _p(g1), _p(be1), _p(h), BF16, M, D, W1.shape[0], 1e-5, _s())
+        _count()
+        hs, zs, means, rstds, wbs = [h], [], [], [], []
+        for (W, b, g, be) in ((W2, b2, g2, be2), (W3, b3, g3, be3), (W4, b4, g4, be4)):
+            Nn, K = W.shape
+            wb = cast_bf16(W)
+            wbs.append(wb)
+            z = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
+            stats = torch.zeros(M, 2, device=dev, dtype=torch.float32)
+            gemm_bf16(hs[-1], wb, M=M, N=Nn, K=K, bias=b, out=z, rowstats=stats)
+            mean = torch.empty(M, device=dev, dtype=torch.float32)
+            rstd = torch.empty(M, device=dev, dtype=torch.float32)
+            call("wf_stats_finalize", _p(stats), M, Nn, 1e-5, _p(mean), _p(rstd), _s())
+            hn = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
+            call("wf_ln_act_fwd", _p(z), BF16, _p(g), _p(be), ACT_RELU, None, None, 1.0, _p(hn), BF16, _p(mean), _p(rstd),
+                 1, M, Nn, 1e-5, _s())
+            _count(2)
+            hs.append(hn); zs.append(z); means.append(mean); rstds.append(rstd)
+        w5b = cast_bf16(W5)
+        pf = torch.empty(M, W5.shape[0], device=dev, dtype=torch.float32)
+        gemm_bf16(hs[-1], w5b, M=M, N=W5.shape[0], K=W5.shape[1], bias=b5, out=pf)
+        pooled = PoolPoints.forward(_Scratch(), pf.view(B, N, -1), mask, valid)
+        max_m, avg_m, max_u, mean_u, arg_m, arg_u = pooled
+        ctx.save_for_backward(x, mask, valid, arg_m, arg_u, *hs, *zs, *means, *rstds, *params)
+        ctx.dims = (B, N, D)
+        ctx.mark_non_differentiable(arg_m, arg_u)
+        pf_out = pf.view(B, N, -1) if want_pf else pf.new_empty(0)
+        return max_m, avg_m, max_u, mean_u, arg_m, arg_u, pf_out
+
+    @staticmethod
+    def backward(ctx, g_max_m, g_avg_m, g_max_u, g_mean_u, _a, _b, g_pf):
+        sv = ctx.saved_tensors
+        x, mask, valid, arg_m, arg_u = sv[:5]
+        hs = sv[5:9]; zs = sv[9:12]; means = sv[12:15]; rstds = sv[15:18]
+        (W1, b1, g1, be1, W2, b2, g2, be2, W3, b3, g3, be3, W4, b4, g4, be4, W5, b5) = sv[18:]
+        B, N, D = ctx.dims
+        M = B * N
+        dev = x.device
+        f = lambda g: None if g is None else _f32c(g)
+        C5 = W5.shape[0]
+        dz = torch.empty(M, C5, device=dev, dtype=torch.bfloat16)
+        call("wf_pool_bwd", _p(f(g_max_m)), _p(f(g_avg_m)), _p(f(g_max_u)), _p(f(g_mean_u)), _p(arg_m), _p(arg_u),
+             _p(mask), _p(valid), B, N, C5, _p(dz), BF16, _s())
+        _count()
+        if g_pf is not None and g_pf.numel() > 0:
+            dz = (dz.float() + g_pf.reshape(M, C5)).to(torch.bfloat16)      # only when a caller used point_features
+        grads = {}
+        sms = _sm_count()
+
+        def weight_grad(dzl, hin, Nn, K):
+            dW = torch.zeros(Nn, K, device=dev, dtype=torch.float32)
+            tiles = ((Nn + 127) // 128) * ((K + 255) // 256)
+            split = max(1, min((M + 63) // 64, (2 * sms + tiles - 1) // tiles))
+            gemm_bf16(dzl, hin, M=Nn, N=K, K=M, kmajor=False, out=dW, accumulate=True, split_k=split)
+            return dW
+
+        # layer 5 (no LayerNorm)
+        grads["W5"] = weight_grad(dz, hs[3], C5, W5.shape[1])
+        grads["b5"] = colsum(dz)
+        dh = torch.empty(M, W5.shape[1], device=dev, dtype=torch.bfloat16)
+        gemm_bf16(dz, cast_bf16(W5, transpose=True), M=M, N=W5.shape[1], K=C5, out=dh)
+        for li, (W, g, be) in zip((2, 1, 0), ((W4, g4, be4), (W3, g3, be3), (W2, g2, be2))):
+            Nn, K = W.shape
+            dzl = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
+            dg = torch.zeros(Nn, device=dev, dtype=torch.float32)
+            dbe = torch.zeros(Nn, device=dev, dtype=torch.float32)
+            db = torch.zeros(Nn, device=dev, dtype=torch.float32)
+            call("wf_ln_act_bwd", _p(dh), BF16, _p(zs[li]), BF16, _p(g), _p(be), _p(means[li]), _p(rstds[li]), ACT_RELU,
+                 None, 1.0, _p(dzl), BF16, _p(dg), _p(dbe), _p(db), M, Nn, _s())
+            _count()
+            k = li + 2
+            grads[f"g{k}"], grads[f"be{k}"], grads[f"b{k}"] = dg, dbe, db
+            grads[f"W{k}"] = weight_grad(dzl, hs[li], Nn, K)
+            dh = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+            gemm_bf16(dzl, cast_bf16(W, transpose=True), M=M, N=K, K=Nn, out=dh)
+        C1 = W1.shape[0]
+        dW1 = torch.zeros(C1, D, device=dev, dtype=torch.float32)
+        db1 = torch.zeros(C1, device=dev, dtype=torch.float32)
+        dg1 = torch.zeros(C1, device=dev, dtype=torch.float32)
+        dbe1 = torch.zeros(C1, device=dev, dtype=torch.float32)
+        dx = torch.empty(M, D, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        call("wf_enc_l1_bwd", _p(x), _p(_f32c(W1)), _p(b1), _p(g1), _p(be1), _p(dh), BF16, _p(dW1), _p(db1), _p(dg1),
+             _p(dbe1), _p(dx), M, D, C1, 1e-5, _s())
+        _count()
+        grads.update(W1=dW1, b1=db1, g1=dg1, be1=dbe1)
+        order = ["W1", "b1", "g1", "be1", "W2", "b2", "g2", "be2", "W3", "b3", "g3", "be3", "W4", "b4", "g4", "be4",
+                 "W5", "b5"]
+        return (None if dx is None else dx.view(B, N, D), None, *[grads[k] for k in order])
+
+
+class _Scratch:
+    """Stand-in ctx for calling a Function's forward as a plain kernel sequence."""
+
+    def save_for_backward(self, *a):
+        pass
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
+# ----------------------------------------------------------------------------------------------
+# vertex head tail
+# ----------------------------------------------------------------------------------------------
+class VertexSplit(torch.autograd.Function):
+    """models/VertexPredictor.py:117-127."""
+
+    @staticmethod
+    def forward(ctx, vf, V):
+        _need_cuda(vf)
+        vf = _f32c(vf)
+        B = vf.shape[0]
+        coords = torch.empty(B, V, 3, device=vf.device, dtype=torch.float32)
+        prob = torch.empty(B, V, device=vf.device, dtype=torch.float32)
+        count = torch.empty(B, device=vf.device, dtype=torch.int64)
+        call("wf_vertex_split_fwd", _p(vf), B, V, _p(coords), _p(prob), _p(count), _s())
+        _count()
+        ctx.save_for_backward(prob)
+        ctx.V = V
+        ctx.mark_non_differentiable(count)
+        return coords, prob, count
+
+    @staticmethod
+    def backward(ctx, d_coords, d_prob, _c):
+        (prob,) = ctx.saved_tensors
+        B, V = prob.shape
+        d_vf = torch.empty(B, V * 4, device=prob.device, dtype=torch.float32)
+        f = lambda g: None if g is None else _f32c(g)
+        call("wf_vertex_split_bwd", _p(f(d_coords)), _p(f(d_prob)), _p(prob), B, V, _p(d_vf), _s())
+        _count()
+        return d_vf, None
+
+
+# ----------------------------------------------------------------------------------------------
+# edge head (ragged)
+# ----------------------------------------------------------------------------------------------
+class Ragged:
+    """Host-known per-sample vertex counts -> CSR offsets on the device."""
+
+    def __init__(self, counts: Sequence[int], device):
+        self.counts = [int(c) for c in counts]
+        B = len(self.counts)
+        v_off = [0] * (B + 1); e_off = [0] * (B + 1); p_off = [0] * (B + 1)
+        for b, c in enumerate(self.counts):
+            v_off[b + 1] = v_off[b] + c
+            e_off[b + 1] = e_off[b] + c * (c - 1) // 2
+            p_off[b + 1] = p_off[b] + 8 * c * c
+        self.B, self.T, self.E, self.Ptot = B, v_off[B], e_off[B], p_off[B]
+        self.max_c = max(self.counts) if self.counts else 0
+        self.max_e = self.max_c * (self.max_c - 1) // 2
+        self.v_off = torch.tensor(v_off, dtype=torch.int32).to(device, non_blocking=True)
+        self.e_off = torch.tensor(e_off, dtype=torch.int64).to(device, non_blocking=True)
+        self.p_off = torch.tensor(p_off, dtype=torch.int64).to(device, non_blocking=True)
+
+
+class GatherPrefix(torch.autograd.Function):
+    """verts[b, :count_b] for all b, packed -- models/PointCloudToWireframe.py:81,91."""
+
+    @staticmethod
+    def forward(ctx, verts, rg: Ragged):
+        _need_cuda(verts)
+        verts = _f32c(verts)
+        B, V, _ = verts.shape
+        out = torch.empty(rg.T, 3, device=verts.device, dtype=torch.float32)
+        call("wf_gather_prefix", _p(verts), B, V, _p(rg.v_off), rg.T, _p(out), _s())
+        _count()
+        ctx.rg = rg; ctx.shape = (B, V)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_packed):
+        B, V = ctx.shape
+        d = torch.zeros(B, V, 3, device=d_packed.device, dtype=torch.float32)
+        call("wf_scatter_prefix_add", _p(_f32c(d_packed)), B, V, _p(ctx.rg.v_off), ctx.rg.T, _p(d), _s())
+        _count()
+        return d, None
+
+
+class AttentionCore(torch.autograd.Function):
+    """softmax(q k^T / sqrt(d)) v for 8 heads, per sample -- the core of nn.MultiheadAttention
+    (models/EdgePredictor.py:109-111); in_proj / out_proj are LinearLNAct calls around it."""
+
+    @staticmethod
+    def forward(ctx, qkv, rg: Ragged, keep, keep_scale):
+        _need_cuda(qkv)
+        qkv = _f32c(qkv)
+        E = qkv.shape[1] // 3
+        out = torch.empty(rg.T, E, device=qkv.device, dtype=torch.float32)
+        probs = torch.empty(rg.Ptot, device=qkv.device, dtype=torch.float32)
+        call("wf_attn_fwd", _p(qkv), _p(rg.v_off), _p(rg.p_off), rg.B, 8, E // 8, rg.max_c, _p(out), _p(probs), _p(keep),
+             float(keep_scale), _s())
+        _count()
+        ctx.save_for_backward(qkv, probs, keep)
+        ctx.rg = rg; ctx.keep_scale = keep_scale
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, probs, keep = ctx.saved_tensors
+        rg = ctx.rg
+        E = qkv.shape[1] // 3
+        d_qkv = torch.empty_like(qkv)
+        call("wf_attn_bwd", _p(_f32c(d_out)), _p(qkv), _p(probs), _p(rg.v_off), _p(rg.p_off), rg.B, 8, E // 8, rg.max_c,
+             _p(d_qkv), _p(keep), float(ctx.keep_scale), _s())
+        _count()
+        return d_qkv, None, None, None
+
+
+class EdgePairLayer(torch.autograd.Function):
+    """z1[e=(i,j)] = P[i] + Q[j] + wd * |v_i - v_j| + b  (models/EdgePredictor.py:117-134 + edge_mlp.0
+    without the (E,1031) concat)."""
+
+    @staticmethod
+    def forward(ctx, P, Q, verts, wd, bias, rg: Ragged):
+        _need_cuda(P)
+        P, Q, verts, wd, bias = _f32c(P), _f32c(Q), _f32c(verts), _f32c(wd), _f32c(bias)
+        C = P.shape[1]
+        z1 = torch.empty(rg.E, C, device=P.device, dtype=torch.float32)
+        dist = torch.empty(rg.E, device=P.device, dtype=torch.float32)
+        call("wf_edge_pair_fwd", _p(P), _p(Q), _p(verts), _p(wd), _p(bias), _p(rg.v_off), _p(rg.e_off), rg.B, rg.T, C,
+             _p(z1), _p(dist), _s())
+        _count()
+        ctx.save_for_backward(dist, verts, wd)
+        ctx.rg = rg
+        return z1
+
+    @staticmethod
+    def backward(ctx, dz1):
+        dist, verts, wd = ctx.saved_tensors
+        rg = ctx.rg
+        C = wd.shape[0]
+        dz1 = _f32c(dz1)
+        dP = torch.empty(rg.T, C, device=dz1.device, dtype=torch.float32)
+        dQ = torch.empty(rg.T, C, device=dz1.device, dtype=torch.float32)
+        dv = torch.zeros(rg.T, 3, device=dz1.device, dtype=torch.float32)
+        dwd = torch.zeros(C, device=dz1.device, dtype=torch.float32)
+        call("wf_edge_pair_bwd", _p(dz1), _p(dist), _p(verts), _p(wd), _p(rg.v_off), _p(rg.e_off), rg.B, rg.T, C, _p(dP),
+             _p(dQ), _p(dv), _p(dwd), _s())
+        _count()
+        dbias = colsum(dP)
+        return dP, dQ, dv, dwd, dbias, None
+
+
+class EdgeOut(torch.autograd.Function):
+    """edge_mlp.10 (128 -> 1) + sigmoid, written zero-padded as (B, max_e):
+    models/EdgePredictor.py:137-138, models/PointCloudToWireframe.py:103-112."""
+
+    @staticmethod
+    def forward(ctx, h, w, bias, rg: Ragged):
+        _need_cuda(h)
+        h, w, bias = _f32c(h), _f32c(w).reshape(-1), _f32c(bias)
+        probs = torch.empty(rg.B, rg.max_e, device=h.device, dtype=torch.float32)
+        call("wf_edge_out_fwd", _p(h), _p(w), _p(bias), _p(rg.e_off), rg.B, w.shape[0], rg.max_e, _p(probs), _s())
+        _count()
+        ctx.save_for_backward(h, w, probs)
+        ctx.rg = rg
+        return probs
+
+    @staticmethod
+    def backward(ctx, d_probs):
+        h, w, probs = ctx.saved_tensors
+        rg = ctx.rg
+        dh = torch.empty_like(h)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(1, device=h.device, dtype=torch.float32)
+        call("wf_edge_out_bwd", _p(_f32c(d_probs)), _p(probs), _p(h), _p(w), _p(rg.e_off), rg.B, w.shape[0], rg.max_e,
+             _p(dh), _p(dw), _p(db), _s())
+        _count()
+        return dh, dw.reshape(1, -1), db, None
+
+
+# ----------------------------------------------------------------------------------------------
+# matching + loss
+# ----------------------------------------------------------------------------------------------
+def loss_match(pred_v, pred_e, tgt_v, counts, want_cost: bool = False):
+    """losses/WireframeLoss.py:106-246 on the device.  Returns (col_of_row[B,V] int32, status[B] int32, cost|None)."""
+    _need_cuda(pred_v)
+    pv, pe, tv = _f32c(pred_v.detach()), _f32c(pred_e.detach()), _f32c(tgt_v)
+    B, V, _ = pv.shape
+    Vt = tv.shape[1]
+    cnt = counts.to(device=pv.device, dtype=torch.int64).contiguous()
+    col = torch.empty(B, V, device=pv.device, dtype=torch.int32)
+    status = torch.empty(B, device=pv.device, dtype=torch.int32)
+    cost = torch.empty(B, V, V, device=pv.device, dtype=torch.float32) if want_cost else None
+    call("wf_loss_match", _p(pv), _p(pe), _p(tv), _p(cnt), B, V, Vt, _p(col), _p(status), _p(cost), _s())
+    _count()
+    return col, status, cost
+
+
+def lsap_batched(cost: torch.Tensor, nr: torch.Tensor, nc: torch.Tensor):
+    """cost [B, max_nr, ld] fp32 on the device; nr/nc int32 [B].  Returns (col_of_row [B,max_nr], status [B])."""
+    _need_cuda(cost)
+    cost = _f32c(cost)
+    B, max_nr, ld = cost.shape
+    max_nc = int(ld)
+    col = torch.empty(B, max_nr, device=cost.device, dtype=torch.int32)
+    status = torch.empty(B, device=cost.device, dtype=torch.int32)
+    call("wf_lsap_batched", _p(cost), max_nr * ld, ld, _p(nr), _p(nc), B, max_nr, max_nc, _p(col), _p(status), _s())
+    _count()
+    return col, status
+
+
+class WireframeLossFn(torch.autograd.Function):
+    """losses/WireframeLoss.py:38-104,248-283: returns (total, vertex, existence, edge)."""
+
+    @staticmethod
+    def forward(ctx, pred_v, pred_e, edge_p, tgt_v, tgt_e, edge_l, col_of_row, counts, wv, we, wx):
+        _need_cuda(pred_v)
+        pv, pe, ep = _f32c(pred_v), _f32c(pred_e), _f32c(edge_p)
+        tv, te, el = _f32c(tgt_v), _f32c(tgt_e), _f32c(edge_l)
+        B, V, _ = pv.shape
+        Ep = ep.shape[1] if ep.dim() == 2 else 0
+        El = el.shape[1] if el.dim() == 2 else 0
+        if ep.numel() == 0 or el.numel() == 0:
+            Ep_eff, El_eff = (Ep, 0) if el.numel() == 0 else (0, El)
+        else:
+            Ep_eff, El_eff = Ep, El
+        out = torch.empty(call("wf_loss_out_floats"), device=pv.device, dtype=torch.float32)
+        cnt = counts.to(device=pv.device, dtype=torch.int64).contiguous()
+        call("wf_loss_fwd", _p(pv), _p(pe), _p(ep), _p(tv), _p(te), _p(el), _p(col_of_row), _p(cnt), B, V, tv.shape[1],
+             Ep_eff if Ep_eff else 0, El_eff if El_eff else 0, float(wv), float(we), float(wx), _p(out), _s())
+        _count(2)
+        ctx.save_for_backward(pv, pe, ep, tv, te, el, col_of_row, cnt, out)
+        ctx.meta = (B, V, tv.shape[1], Ep, El, Ep_eff, El_eff, wv, we, wx)
+        return out[0], out[1], out[2], out[3]
+
+    @staticmethod
+    def backward(ctx, g_t, g_v, g_x, g_e):
+        pv, pe, ep, tv, te, el, col, cnt, out = ctx.saved_tensors
+        B, V, Vt, Ep, El, Ep_eff, El_eff, wv, we, wx = ctx.meta
+        z = lambda g: torch.zeros((), device=pv.device) if g is None else g.reshape(()).float()
+        g_out = torch.stack([z(g_t), z(g_v), z(g_x), z(g_e)]).contiguous()
+        d_pv = torch.empty_like(pv); d_pe = torch.empty_like(pe); d_ep = torch.empty_like(ep)
+        # Ep_eff/El_eff are 0 when either side is empty (edge term off); d_edge_p must still be zero-filled
+        if Ep_eff == 0 or El_eff == 0:
+            d_ep.zero_()
+            call("wf_loss_bwd", _p(g_out), _p(pv), _p(pe), _p(ep), _p(tv), _p(te), _p(el), _p(col), _p(cnt), _p(out), B, V,
+                 Vt, 0, 0, float(wv), float(we), float(wx), _p(d_pv), _p(d_pe), _p(d_ep), _s())
+        else:
+            call("wf_loss_bwd", _p(g_out), _p(pv), _p(pe), _p(ep), _p(tv), _p(te), _p(el), _p(col), _p(cnt), _p(out), B, V,
+                 Vt, Ep, El, float(wv), float(we), float(wx), _p(d_pv), _p(d_pe), _p(d_ep), _s())
+        _count()
+        return d_pv, d_pe, d_ep, None, None, None, None, None, None, None, None
