@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: training samples/s on 10k-point clouds.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference [--gpus N --steps K --warmup W]
+
+A "step" is one pass of the hot path over one batch of synthetic input, exactly the body of the reference's
+training loop (train.py:124-142): zero_grad -> PointCloudToWireframe forward -> WireframeLoss (Hungarian matching
+inside) -> backward -> [gradient all-reduce when N>1] -> clip_grad_norm_(1.0) -> Adam step.
+
+Workload (config.workload): BASELINE.json configs[2] -- data-parallel training, 64 clouds x 10,000 points x 8 features
+per GPU, 64 vertex slots, GT vertex counts ~ U{16..64}, bf16 wide encoder layers (fp32 accumulate), fp32 everything
+else; weak scaling (per-GPU batch fixed, global batch 64*N).  Random-init weights of the reference architecture,
+synthetic data of the reference's shapes (no network for datasets/checkpoints).
+
+One JSON line is printed by rank 0; see README / DESIGN.md for the keys.  The oracle (oracle/) is executed only by
+the `cpu_baseline` leg and by `--impl reference`, as the thing being compared against -- never by the product path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "wireframe-3d-prediction_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+POINTS, VERTS, PER_GPU_BATCH, FEATS = 10000, 64, 64, 8
+FLOP_PER_POINT_TRAIN = 31457280          # wide layers fwd + dX + dW, recompute not counted
+FLOP_PER_POINT_FWD = 10485760
+METRIC = "train samples/s (10k-pt clouds)"
+UNIT = "samples/s"
+
+
+def workload_name(n_gpus):
+    return (f"train step: {PER_GPU_BATCH} clouds/GPU x {POINTS} pts x {FEATS} feats, {VERTS} vertex slots, "
+            f"counts~U{{16..64}}, global batch {PER_GPU_BATCH * n_gpus} (BASELINE.json configs[2], weak scaling)")
+
+
+def make_batch(rank, B):
+    """Synthetic batch shaped like datasets/building3d.py:109-126 output + train.py:48-88 targets."""
+    from wf_b200.synthetic import make_inputs
+    return make_inputs(seed=rank, B=B, N=POINTS, V=VERTS, min_count=16, max_count=64)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (profiling recipe's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("bf16_tflops"), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+def traffic_from_profile():
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("gemm_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (torch CPU restatement of the reference path), all host threads
+# ----------------------------------------------------------------------------------------------
+def cpu_step_factory(sample_b):
+    from oracle import wireframe_oracle as wo
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.clone().requires_grad_(True) for k, v in wo.make_state_dict(0, VERTS).items()}
+    opt = torch.optim.Adam([v for k, v in sd.items() if "spatial_proj" not in k], lr=1e-3, weight_decay=1e-6)
+    x, tgt, _ = wo.make_inputs(0, sample_b, POINTS, VERTS, min_count=16, max_count=64)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        ld, _ = wo.train_step(sd, x, tgt, max_vertices=VERTS)
+        torch.nn.utils.clip_grad_norm_([v for v in sd.values() if v.grad is not None], 1.0)
+        opt.step()
+        return float(ld["total_loss"])
+    return step
+
+
+def run_cpu(steps, warmup, sample_b):
+    step = cpu_step_factory(sample_b)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample_b * steps / dt, dt / steps * 1e3
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                   # rank 0 alone runs the CPU arm
+    sample_b = 2
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    val, ms = run_cpu(steps, warmup, sample_b)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "note": "CPU arm: bounded sample per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_b} clouds x {POINTS} pts per step (full fwd+loss+bwd+clip+Adam), "
+                                   f"{steps} steps after {warmup} warm-up, torch {torch.__version__} CPU, {cores} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main_gpu(args):
+    import torch.distributed as dist
+    from wf_b200 import ops, load
+    from wf_b200.parallel import GradAllReduce, shard_loss_weights
+    from models.PointCloudToWireframe import PointCloudToWireframe
+    from losses.WireframeLoss import WireframeLoss
+    load()                                         # fail loudly if the CUDA library is missing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision("bf16")
+
+    torch.manual_seed(0)                           # same weights on every rank
+    model = PointCloudToWireframe(input_dim=FEATS, max_vertices=VERTS).to(dev)
+    model.train()
+    crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)      # train.py:90-94
+    B = PER_GPU_BATCH
+    x_host, tgt_host, counts_host = make_batch(rank, B)
+    x_pin = x_host.pin_memory()
+    tgt_pin = {k: v.pin_memory() for k, v in tgt_host.items()}
+    x = x_pin.to(dev, non_blocking=True)
+    tgt = {k: v.to(dev, non_blocking=True) for k, v in tgt_pin.items()}
+    counts = tgt["vertex_counts"]
+    all_counts = [make_counts_only(r, B) for r in range(world)]
+    wv, wx, we = shard_loss_weights(counts_host.tolist(), all_counts, VERTS)
+
+    # materialise the lazy point_pool_proj before the optimizer exists, so DP replicas stay identical
+    with torch.no_grad():
+        model(x[:2, :256], counts[:2])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-6, eps=1e-8, betas=(0.9, 0.999))   # train.py:96
+    reducer = GradAllReduce(model)
+
+    def step(xin, targets, want_loss):
+        reducer.zero()
+        pred = model(xin, targets["vertex_counts"])
+        ld = crit(pred, targets)
+        loss = (3.0 * wv) * ld["vertex_loss"] + (1.5 * wx) * ld["existence_loss"] + (1.0 * we) * ld["edge_loss"] \
+            if world > 1 else ld["total_loss"]
+        loss.backward()
+        reducer.finish()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        return loss.item() if want_loss else None
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        total_ms = 0.0
+        for _ in range(n):
+            flush.fill_(1)                                                  # L2 flush, outside the timed region
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if e2e:
+                xin = x_pin.to(dev, non_blocking=True)                      # H2D of this step's inputs (pinned)
+                tg = {k: v.to(dev, non_blocking=True) for k, v in tgt_pin.items()}
+                step(xin, tg, True)                                         # D2H: the loss scalar
+            else:
+                step(x, tgt, False)
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        return total_ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(x, tgt, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: device-resident inputs, kernel-level GEMM timing on the launching stream
+    ops.GEMM_PROFILE = []
+    l0 = ops.LAUNCHES
+    barrier()
+    ms = timed(args.steps, e2e=False)
+    barrier()
+    launches = ops.LAUNCHES - l0
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- timed region 2: end to end through the public API with host buffers
+    barrier()
+    ms_e2e = timed(args.steps, e2e=True)
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    gemm_flop = sum(f for _, _, f in prof)
+    if rank == 0:
+        sustained, burst, src = peaks()
+        samples = B * world * args.steps
+        h2d = x_pin.numel() * 4 + sum(v.numel() * v.element_size() for v in tgt_pin.values())
+        achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": samples / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(world), "parallelism": f"dp{world}",
+                       "l2": "256 MB buffer written between timed steps (outside the events); per-step working set ~11 GB",
+                       "precision": "bf16 operands / fp32 accumulate on encoder layers 2-5, fp32 elsewhere",
+                       "dropout": "enabled (edge head, p=0.1)"},
+            "clocks": clocks,
+            "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "wf::tc::gemm_bf16_kernel (12 launches/step: 4 fwd + 4 dX + 4 dW)", "bound": "tensor",
+                         "achieved": achieved, "peak": sustained, "peak_burst": burst, "peak_source": src,
+                         "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None,
+                         "traffic": traffic_from_profile(),
+                         "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / ms if ms else None,
+                         "flop_per_launch_avg": gemm_flop / max(1, len(prof)),
+                         "encoder_train_mpts_per_s": (B * POINTS * args.steps) / (ms * 1e-3) / 1e6},
+        }
+        if world == 1 and not args.no_cpu:
+            v, cms = run_cpu(steps=3, warmup=1, sample_b=2)
+            cores = os.cpu_count() or 1
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"oracle port, 2 clouds x {POINTS} pts per step, 3 steps after 1 warm-up "
+                                              f"({cms:.0f} ms/step), torch CPU {cores} threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def make_counts_only(rank, B):
+    from wf_b200.synthetic import make_counts
+    return make_counts(seed=rank, B=B, V=VERTS, min_count=16, max_count=64)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="wf_b200", choices=["wf_b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_gpu(a)

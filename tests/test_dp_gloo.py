@@ -1,0 +1,133 @@
+"""Data-parallel host logic on CPU (gloo, world_size 2): the bucketed gradient all-reduce and the batch-global
+loss normalisation.  The loss here is the oracle's (CPU); the product's reducer and
+shard_loss_weights are the code under test."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+class TinyHead(torch.nn.Module):
+    """x (B, F) -> predictions dict with the same fields/semantics the real model emits."""
+
+    def __init__(self, F, V, max_e):
+        super().__init__()
+        self.v = torch.nn.Linear(F, V * 3)
+        self.e = torch.nn.Linear(F, V)
+        self.g = torch.nn.Linear(F, max_e)
+        self.unused = torch.nn.Linear(3, 3)          # never used -> grad None (like EdgePredictor.spatial_proj)
+        self.V = V
+
+    def forward(self, x, counts):
+        B = x.shape[0]
+        verts = self.v(x).reshape(B, self.V, 3)
+        ex = torch.sigmoid(self.e(x))
+        ne = [int(c) * (int(c) - 1) // 2 for c in counts]
+        me = max(ne)
+        ep = torch.sigmoid(self.g(x))[:, :me]
+        mask = torch.zeros(B, me)
+        for b, n in enumerate(ne):
+            mask[b, :n] = 1.0
+        return {"vertices": verts, "existence_probabilities": ex, "edge_probs": ep * mask}
+
+
+def _data(V):
+    rng = np.random.default_rng(0)
+    B, F = 6, 10
+    counts = [3, 7, 2, 5, 8, 4]
+    x = torch.from_numpy(rng.normal(size=(B, F)).astype(np.float32))
+    tv = torch.zeros(B, V, 3); te = torch.zeros(B, V)
+    for b, c in enumerate(counts):
+        tv[b, :c] = torch.from_numpy(rng.uniform(-1, 1, (c, 3)).astype(np.float32)); te[b, :c] = 1
+    max_e = max(c * (c - 1) // 2 for c in counts)
+    el = torch.from_numpy((rng.uniform(size=(B, max_e)) < 0.3).astype(np.float32))
+    for b, c in enumerate(counts):
+        el[b, c * (c - 1) // 2:] = 0
+    return x, counts, tv, te, el, max_e
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, "wireframe-3d-prediction_b200")); sys.path.insert(0, ROOT)
+    from oracle import wireframe_oracle as wo
+    from wf_b200.parallel import GradAllReduce, shard_loss_weights
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    V = 8
+    x, counts, tv, te, el, max_e = _data(V)
+    torch.manual_seed(0)
+    model = TinyHead(x.shape[1], V, max_e)
+    shards = [[0, 1, 2, 3], [4, 5]]                       # unequal shards on purpose
+    idx = shards[rank]
+    red = GradAllReduce(model, bucket_bytes=256)         # tiny buckets -> several all-reduces
+    w = (3.0, 1.0, 1.5)
+    res = []
+    for step in range(3):                                 # step 0 builds the buckets, later steps use the hooks
+        red.zero()
+        lc = [counts[i] for i in idx]
+        pred = model(x[idx], lc)
+        me_local = max(c * (c - 1) // 2 for c in lc)
+        tgt = {"vertices": tv[idx], "vertex_existence": te[idx], "edge_labels": el[idx][:, :me_local],
+               "vertex_counts": torch.tensor(lc)}
+        ld = wo.loss_forward(pred, tgt, *w)
+        sv, sx, se = shard_loss_weights(lc, [[counts[i] for i in s] for s in shards], V)
+        loss = w[0] * sv * ld["vertex_loss"] + w[2] * sx * ld["existence_loss"] + w[1] * se * ld["edge_loss"]
+        loss.backward()
+        red.finish()
+        res.append({k: (None if p.grad is None else p.grad.detach().clone()) for k, p in model.named_parameters()})
+    if rank == 0:
+        # single-process full-batch reference
+        torch.manual_seed(0)
+        ref = TinyHead(x.shape[1], V, max_e)
+        pred = ref(x, counts)
+        tgt = {"vertices": tv, "vertex_existence": te, "edge_labels": el, "vertex_counts": torch.tensor(counts)}
+        wo.loss_forward(pred, tgt, *w)["total_loss"].backward()
+        ok = True
+        for r in res:
+            for k, p in ref.named_parameters():
+                if p.grad is None:
+                    ok &= r[k] is None
+                else:
+                    ok &= bool(torch.allclose(r[k], p.grad, rtol=1e-4, atol=1e-6))
+        out.put(ok)
+    g0 = torch.cat([g.reshape(-1) for g in res[-1].values() if g is not None])
+    gathered = [torch.zeros_like(g0) for _ in range(world)]
+    dist.all_gather(gathered, g0)
+    if rank == 0:
+        out.put(bool(torch.equal(gathered[0], gathered[1])))
+    dist.destroy_process_group()
+
+
+def test_sharded_gradients_equal_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True, "sum of rescaled shard gradients != full-batch gradient"
+    assert q.get(timeout=10) is True, "ranks disagree after all-reduce"
+
+
+def test_shard_loss_weights_sum_rules():
+    sys.path.insert(0, os.path.join(ROOT, "wireframe-3d-prediction_b200"))
+    from wf_b200.parallel import shard_loss_weights
+    allc = [[3, 7, 2, 5], [8, 4]]
+    ws = [shard_loss_weights(c, allc, 8) for c in allc]
+    assert abs(sum(w[0] for w in ws) - 1.0) < 1e-12 and abs(sum(w[1] for w in ws) - 1.0) < 1e-12
+    # edge: (B_r * maxE_r) / (B * maxE)
+    assert abs(ws[0][2] - (4 * 21) / (6 * 28)) < 1e-12 and abs(ws[1][2] - (2 * 28) / (6 * 28)) < 1e-12

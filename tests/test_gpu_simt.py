@@ -234,10 +234,10 @@ def test_edge_pair_and_out(ops):
     assert_close(z, z_ref, 1e-5, "pair fwd")
     h = ops.linear_ln_act(z, f[5], None, None, None, 2)
     out = ops.EdgeOut.apply(h, f[6], f[7], rg)
-    assert_close(out, padded, 1e-5, "edge out fwd")
+    assert_close(out, padded, 1e-4, "edge out fwd")
     out.backward(go.float())
     for n, a, r in zip("P Q verts wd bias Wm w_out b_out".split(), f, leaves):
-        assert_close(a.grad, r.grad, 1e-4, f"edge grad {n}")
+        assert_close(a.grad, r.grad, 3e-4, f"edge grad {n}")
 
 
 def test_gather_prefix_and_vertex_split(ops):

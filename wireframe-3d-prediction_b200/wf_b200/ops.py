@@ -249,8 +249,10 @@ class PoolPoints(torch.autograd.Function):
         arg_m, arg_u, mask, valid = ctx.saved_tensors
         B, N, C = ctx.shape
         d_pf = torch.empty(B, N, C, device=mask.device, dtype=torch.float32)
-        f = lambda g: None if g is None else _f32c(g)
-        call("wf_pool_bwd", _p(f(g_max_m)), _p(f(g_avg_m)), _p(f(g_max_u)), _p(f(g_mean_u)), _p(arg_m), _p(arg_u),
+        # keep the (possibly re-laid-out) gradient tensors alive until the launch: a raw pointer taken from a
+        # temporary would dangle once the caching allocator hands the block to the next temporary
+        gs = [None if g is None else _f32c(g) for g in (g_max_m, g_avg_m, g_max_u, g_mean_u)]
+        call("wf_pool_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u),
              _p(mask), _p(valid), B, N, C, _p(d_pf), F32, _s())
         _count()
         return d_pf, None, None
@@ -259,11 +261,21 @@ class PoolPoints(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # encoder per-point MLP on tensor cores (bf16 operands, fp32 accumulate) fused with the pools
 # ----------------------------------------------------------------------------------------------
+GEMM_PROFILE = None   # bench.py sets this to a list: (start event, end event, algorithmic FLOPs) per wf_gemm_bf16 launch
+
+
 def gemm_bf16(A, B, *, M, N, K, kmajor=True, bias=None, out, accumulate=False, split_k=1, rowstats=None):
     lda = A.stride(0)
     ldb = B.stride(0)
+    prof = GEMM_PROFILE
+    if prof is not None:                      # CUDA events on the launching stream, around this kernel only
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("wf_gemm_bf16", _p(A), lda, int(kmajor), _p(B), ldb, int(kmajor), M, N, K, _p(bias), _p(out), out.stride(0),
          _dt(out), int(accumulate), int(split_k), _p(rowstats), _s())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K))
     _count()
     return out
 
@@ -300,7 +312,8 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         dev = x.device
         mask, valid = point_mask(x)
         h = torch.empty(M, W1.shape[0], device=dev, dtype=torch.bfloat16)
-        call("wf_enc_l1_fwd", _p(x), _p(_f32c(W1)), _p(b1), _p(g1), _p(be1), _p(h), BF16, M, D, W1.shape[0], 1e-5, _s())
+        W1c = _f32c(W1)
+        call("wf_enc_l1_fwd", _p(x), _p(W1c), _p(b1), _p(g1), _p(be1), _p(h), BF16, M, D, W1.shape[0], 1e-5, _s())
         _count()
         hs, zs, means, rstds, wbs = [h], [], [], [], []
         for (W, b, g, be) in ((W2, b2, g2, be2), (W3, b3, g3, be3), (W4, b4, g4, be4)):
@@ -338,10 +351,10 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         B, N, D = ctx.dims
         M = B * N
         dev = x.device
-        f = lambda g: None if g is None else _f32c(g)
+        gs = [None if g is None else _f32c(g) for g in (g_max_m, g_avg_m, g_max_u, g_mean_u)]   # held until the launch
         C5 = W5.shape[0]
         dz = torch.empty(M, C5, device=dev, dtype=torch.bfloat16)
-        call("wf_pool_bwd", _p(f(g_max_m)), _p(f(g_avg_m)), _p(f(g_max_u)), _p(f(g_mean_u)), _p(arg_m), _p(arg_u),
+        call("wf_pool_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u),
              _p(mask), _p(valid), B, N, C5, _p(dz), BF16, _s())
         _count()
         if g_pf is not None and g_pf.numel() > 0:
@@ -381,7 +394,8 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         dg1 = torch.zeros(C1, device=dev, dtype=torch.float32)
         dbe1 = torch.zeros(C1, device=dev, dtype=torch.float32)
         dx = torch.empty(M, D, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
-        call("wf_enc_l1_bwd", _p(x), _p(_f32c(W1)), _p(b1), _p(g1), _p(be1), _p(dh), BF16, _p(dW1), _p(db1), _p(dg1),
+        W1c = _f32c(W1)
+        call("wf_enc_l1_bwd", _p(x), _p(W1c), _p(b1), _p(g1), _p(be1), _p(dh), BF16, _p(dW1), _p(db1), _p(dg1),
              _p(dbe1), _p(dx), M, D, C1, 1e-5, _s())
         _count()
         grads.update(W1=dW1, b1=db1, g1=dg1, be1=dbe1)
@@ -426,8 +440,9 @@ class VertexSplit(torch.autograd.Function):
         (prob,) = ctx.saved_tensors
         B, V = prob.shape
         d_vf = torch.empty(B, V * 4, device=prob.device, dtype=torch.float32)
-        f = lambda g: None if g is None else _f32c(g)
-        call("wf_vertex_split_bwd", _p(f(d_coords)), _p(f(d_prob)), _p(prob), B, V, _p(d_vf), _s())
+        dc = None if d_coords is None else _f32c(d_coords)
+        dp = None if d_prob is None else _f32c(d_prob)
+        call("wf_vertex_split_bwd", _p(dc), _p(dp), _p(prob), B, V, _p(d_vf), _s())
         _count()
         return d_vf, None
 
@@ -472,7 +487,8 @@ class GatherPrefix(torch.autograd.Function):
     def backward(ctx, d_packed):
         B, V = ctx.shape
         d = torch.zeros(B, V, 3, device=d_packed.device, dtype=torch.float32)
-        call("wf_scatter_prefix_add", _p(_f32c(d_packed)), B, V, _p(ctx.rg.v_off), ctx.rg.T, _p(d), _s())
+        dpk = _f32c(d_packed)
+        call("wf_scatter_prefix_add", _p(dpk), B, V, _p(ctx.rg.v_off), ctx.rg.T, _p(d), _s())
         _count()
         return d, None
 
@@ -501,7 +517,8 @@ class AttentionCore(torch.autograd.Function):
         rg = ctx.rg
         E = qkv.shape[1] // 3
         d_qkv = torch.empty_like(qkv)
-        call("wf_attn_bwd", _p(_f32c(d_out)), _p(qkv), _p(probs), _p(rg.v_off), _p(rg.p_off), rg.B, 8, E // 8, rg.max_c,
+        d_out = _f32c(d_out)
+        call("wf_attn_bwd", _p(d_out), _p(qkv), _p(probs), _p(rg.v_off), _p(rg.p_off), rg.B, 8, E // 8, rg.max_c,
              _p(d_qkv), _p(keep), float(ctx.keep_scale), _s())
         _count()
         return d_qkv, None, None, None
@@ -564,7 +581,8 @@ class EdgeOut(torch.autograd.Function):
         dh = torch.empty_like(h)
         dw = torch.zeros_like(w)
         db = torch.zeros(1, device=h.device, dtype=torch.float32)
-        call("wf_edge_out_bwd", _p(_f32c(d_probs)), _p(probs), _p(h), _p(w), _p(rg.e_off), rg.B, w.shape[0], rg.max_e,
+        d_probs = _f32c(d_probs)
+        call("wf_edge_out_bwd", _p(d_probs), _p(probs), _p(h), _p(w), _p(rg.e_off), rg.B, w.shape[0], rg.max_e,
              _p(dh), _p(dw), _p(db), _s())
         _count()
         return dh, dw.reshape(1, -1), db, None
