@@ -148,6 +148,15 @@ int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, i
                  int N, int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate,
                  int split_k, float* rowstats, wf_stream_t stream);
 
+/* bf16 LayerNorm+ReLU passes between the tensor-core layers (models/PointNetEncoder.py:38-39), 16-byte vectorised,
+ * HBM-bound.  fwd: h = relu(LN(z)) with the row statistics from the GEMM epilogue.  bwd: dz from dh and z in ONE pass;
+ * dgamma/dbeta/dcolsum (the Linear's bias gradient) are accumulated (caller zeroes).  C in {512,1024,2048}. */
+int wf_ln_relu_bf16_fwd(const void* z, const float* mean, const float* rstd, const float* gamma,
+                        const float* beta, void* h, int M, int C, wf_stream_t stream);
+int wf_ln_relu_bf16_bwd(const void* dh, const void* z, const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, void* dz, float* dgamma, float* dbeta,
+                        float* dcolsum, int M, int C, wf_stream_t stream);
+
 /* (sum, sumsq) -> (mean, rstd) per row */
 int wf_stats_finalize(const float* rowstats, int M, int C, float eps, float* mean, float* rstd,
                       wf_stream_t stream);

@@ -74,7 +74,6 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
-                assert "oracle" not in src.replace("oracle/", "").lower() or f == "__init__.py" or "wireframe_oracle" not in src, f
                 assert "import oracle" not in src and "from oracle" not in src, f"{f} imports the oracle"
 
 

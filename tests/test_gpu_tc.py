@@ -148,3 +148,30 @@ def test_enc_l1_kernels_fp32_dtype(ops):
     call("wf_enc_l1_bwd", ops._p(x), ops._p(W), ops._p(b), ops._p(g), ops._p(be), ops._p(go32), F32, ops._p(dW2), ops._p(db2),
          ops._p(dg2), ops._p(dbe2), None, M, 8, 512, 1e-5, ops._s())
     assert_close(dW2, d[1].grad, 5e-5, "l1 bwd dW (no dx)")
+
+
+@pytest.mark.parametrize("C", [512, 1024, 2048])
+def test_ln_relu_bf16_kernels(ops, C):
+    """wf_ln_relu_bf16_fwd/bwd against torch autograd (fp64) on the same bf16-rounded inputs and the same row statistics."""
+    import torch.nn.functional as F
+    from wf_b200._lib import call
+    torch.manual_seed(C)
+    M = 1003
+    z = (torch.randn(M, C, device="cuda") * 1.5 + 0.3).to(torch.bfloat16)
+    dh = torch.randn(M, C, device="cuda").to(torch.bfloat16)
+    g = (1 + 0.1 * torch.randn(C, device="cuda")); be = 0.1 * torch.randn(C, device="cuda")
+    zd = z.double().requires_grad_(True); gd = g.double().requires_grad_(True); bd = be.double().requires_grad_(True)
+    mean = zd.detach().mean(1); var = zd.detach().var(1, unbiased=False); rstd = (var + 1e-5).rsqrt()
+    ref = torch.relu(F.layer_norm(zd, (C,), gd, bd, 1e-5))
+    ref.backward(dh.double())
+    m32, r32 = mean.float().contiguous(), rstd.float().contiguous()
+    h = torch.empty_like(z)
+    call("wf_ln_relu_bf16_fwd", ops._p(z), ops._p(m32), ops._p(r32), ops._p(g), ops._p(be), ops._p(h), M, C, ops._s())
+    assert_close(h.float(), ref, 6e-3, "ln fwd bf16")
+    dz = torch.empty_like(z); dg = torch.zeros(C, device="cuda"); dbe = torch.zeros(C, device="cuda"); db = torch.zeros(C, device="cuda")
+    call("wf_ln_relu_bf16_bwd", ops._p(dh), ops._p(z), ops._p(m32), ops._p(r32), ops._p(g), ops._p(be), ops._p(dz), ops._p(dg),
+         ops._p(dbe), ops._p(db), M, C, ops._s())
+    assert_close(dz.float(), zd.grad, 8e-3, "ln bwd dz")
+    assert_close(dg, gd.grad, 1e-4, "ln bwd dgamma")
+    assert_close(dbe, bd.grad, 1e-4, "ln bwd dbeta")
+    assert_close(db, zd.grad.sum(0), 2e-3, "ln bwd colsum(dz)")

@@ -16,7 +16,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                 const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc,
-                const float* __restrict__ bias) {
+                const float* __restrict__ bias, int k_chunk) {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
     const int tid = threadIdx.x;
@@ -28,7 +28,10 @@ gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, i
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += TK) {
+    // split-K: blockIdx.z owns [kz0, kz1) and accumulates atomically (host pre-zeroes C when beta == 0)
+    const int kz0 = blockIdx.z * k_chunk;
+    K = min(K, kz0 + k_chunk);
+    for (int k0 = kz0; k0 < K; k0 += TK) {
         // ---- stage A (op(A) is M x K)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -75,10 +78,15 @@ gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, i
             const int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
             float v = alpha * acc[i][j];
-            if (bias) v += bias[gn];
             float* dst = C + (size_t)gm * ldc + gn;
-            if (beta != 0.f) v += beta * (*dst);
-            *dst = v;
+            if (gridDim.z > 1) {
+                if (bias && blockIdx.z == 0) v += bias[gn];
+                atomicAdd(dst, v);
+            } else {
+                if (bias) v += bias[gn];
+                if (beta != 0.f) v += beta * (*dst);
+                *dst = v;
+            }
         }
     }
 }
@@ -264,10 +272,25 @@ extern "C" int wf_gemm_f32(int transA, int transB, int M, int N, int K, float al
     WF_CHECK_ARG(K >= 0 && lda > 0 && ldb > 0 && ldc >= N, "wf_gemm_f32: bad dims");
     dim3 grid(cdiv(N, TN), cdiv(M, TM));
     cudaStream_t s = as_stream(stream);
-    if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
-    else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
-    else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
-    else gemm_f32_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    // split-K when the output is small and the reduction long (weight gradients of the edge head: K = #edges)
+    int split = 1;
+    const long long ctas = (long long)grid.x * grid.y;
+    if (ctas < sm_count() && K >= 1024 && (beta == 0.f || beta == 1.f)) {
+        split = (int)((2LL * sm_count() + ctas - 1) / ctas);
+        if (split > K / 256) split = K / 256;
+        if (split < 1) split = 1;
+    }
+    int k_chunk = K;
+    if (split > 1) {
+        k_chunk = ((K + split - 1) / split + TK - 1) / TK * TK;
+        split = (K + k_chunk - 1) / k_chunk;
+        if (beta == 0.f) WF_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s));
+    }
+    grid.z = split;
+    if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
+    else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
+    else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
+    else gemm_f32_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

@@ -30,7 +30,9 @@ constexpr int B_BYTES = BN * BK * 2;          // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BOX_BYTES = 64 * 64 * 2;        // one MN-major box
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int STG_LD = 36;                                   // floats per staged row (32 + 4 pad: conflict-free v4 access)
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;               // one 32x32 fp32 staging tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int NTHREADS = 256;
 
@@ -54,7 +56,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));   // inside BAR_BYTES
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = p.tiles_m * p.tiles_n * p.split_k;
@@ -135,11 +137,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
+        // TMEM -> registers (thread = row): + bias, row statistics.  Then through a per-warp 32x32 fp32 staging tile in
+        // shared memory so that global stores are row-contiguous (a quarter warp writes one 128-byte fp32 row segment /
+        // a 64-byte bf16 segment) instead of 32 rows x 16 bytes per instruction.
         const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + q * 32 * STG_LD;
+        const bool bias_v4 = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m;
-            const int row = m_blk * BM + q * 32 + lane;
+            const int row0 = m_blk * BM + q * 32;
+            const int row = row0 + lane;
             const bool row_ok = row < p.M;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
@@ -154,43 +162,69 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 float v[32];
                 const bool full = col0 + 32 <= p.N;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = __uint_as_float(r[j]);
-                    if (p.bias != nullptr && (full || col0 + j < p.N)) v[j] += __ldg(p.bias + col0 + j);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias != nullptr) {
+                    if (full && bias_v4) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                    }
                 }
                 if (p.rowstats != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (full || col0 + j < p.N) { s1 += v[j]; s2 += v[j] * v[j]; }
+                        if (full || col0 + j < p.N) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
                 }
-                if (row_ok) {
-                    if (p.out_dtype == WF_BF16) {
-                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
-                        if (full) {
+                if (full && !p.accumulate) {
+                    // ---- stage, then row-contiguous stores
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    __syncwarp();
+                    if (p.out_dtype == WF_BF16) {
+                        const int rr = lane >> 2, cc = (lane & 3) * 8;         // 4 lanes per row, 8 columns each
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rl = rr + 8 * i;
+                            const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cc);
+                            const float4 b = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cc + 4);
+                            if (row0 + rl < p.M) {
                                 uint4 pk;
-                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
                                 pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
                                 pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                                *reinterpret_cast<uint4*>(dst + j) = pk;
+                                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + (size_t)(row0 + rl) * p.ldd + col0 + cc) = pk;
                             }
-                        } else {
-                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
                         }
+                    } else {
+                        const int rr = lane >> 3, cc = (lane & 7) * 4;         // 8 lanes per row, 4 columns each
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rl = rr + 4 * i;
+                            const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cc);
+                            if (row0 + rl < p.M)
+                                *reinterpret_cast<float4*>(static_cast<float*>(p.D) + (size_t)(row0 + rl) * p.ldd + col0 + cc) = a;
+                        }
+                    }
+                    __syncwarp();
+                } else if (row_ok) {
+                    // ---- column tail or split-K accumulation: direct per-row access
+                    if (p.out_dtype == WF_BF16) {
+                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
                     } else {
                         float* dst = static_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
                         if (p.accumulate) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (full || col0 + j < p.N) atomicAdd(dst + j, v[j]);
-                        } else if (full) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         } else {
                             for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = v[j];
                         }

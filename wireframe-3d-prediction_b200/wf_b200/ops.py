@@ -327,8 +327,7 @@ class EncoderPointMLP_TC(torch.autograd.Function):
             rstd = torch.empty(M, device=dev, dtype=torch.float32)
             call("wf_stats_finalize", _p(stats), M, Nn, 1e-5, _p(mean), _p(rstd), _s())
             hn = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
-            call("wf_ln_act_fwd", _p(z), BF16, _p(g), _p(be), ACT_RELU, None, None, 1.0, _p(hn), BF16, _p(mean), _p(rstd),
-                 1, M, Nn, 1e-5, _s())
+            call("wf_ln_relu_bf16_fwd", _p(z), _p(mean), _p(rstd), _p(g), _p(be), _p(hn), M, Nn, _s())
             _count(2)
             hs.append(hn); zs.append(z); means.append(mean); rstds.append(rstd)
         w5b = cast_bf16(W5)
@@ -380,8 +379,8 @@ class EncoderPointMLP_TC(torch.autograd.Function):
             dg = torch.zeros(Nn, device=dev, dtype=torch.float32)
             dbe = torch.zeros(Nn, device=dev, dtype=torch.float32)
             db = torch.zeros(Nn, device=dev, dtype=torch.float32)
-            call("wf_ln_act_bwd", _p(dh), BF16, _p(zs[li]), BF16, _p(g), _p(be), _p(means[li]), _p(rstds[li]), ACT_RELU,
-                 None, 1.0, _p(dzl), BF16, _p(dg), _p(dbe), _p(db), M, Nn, _s())
+            call("wf_ln_relu_bf16_bwd", _p(dh), _p(zs[li]), _p(means[li]), _p(rstds[li]), _p(g), _p(be), _p(dzl), _p(dg),
+                 _p(dbe), _p(db), M, Nn, _s())
             _count()
             k = li + 2
             grads[f"g{k}"], grads[f"be{k}"], grads[f"b{k}"] = dg, dbe, db
