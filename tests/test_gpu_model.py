@@ -90,7 +90,10 @@ def test_train_step_vs_reference_golden(golden_dir, name, prec):
         # d/d(input) is a 512-term sum with LayerNorm cancellation: not meaningful under bf16 noise, nor in fp32 with
         # un-normalised intensity (the reference's own fp32 value is noise-dominated there)
         if prec == "fp32" and "rawint" not in name:
-            assert_close(xg.grad, torch.from_numpy(g["dx"]), gtol * 2, "dx")
+            # zero-padded points are exact duplicates: which duplicate the max-pool gradient lands on depends on last-bit
+            # rounding inside the reference's MKL GEMM (all parameter gradients are unaffected) -> compare real points only
+            real = (x.abs().sum(-1) > 0)
+            assert_close(xg.grad.cpu()[real], torch.from_numpy(g["dx"])[real], gtol * 2, "dx")
         print(prec, name, "worst grad-norm rel err", worst)
         if prec == "fp32":        # argmax parity: identical except inside fp32 noise
             r = m.encoder.pooled(xg.detach())

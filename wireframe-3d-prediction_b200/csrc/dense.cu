@@ -275,7 +275,8 @@ extern "C" int wf_gemm_f32(int transA, int transB, int M, int N, int K, float al
     // split-K when the output is small and the reduction long (weight gradients of the edge head: K = #edges)
     int split = 1;
     const long long ctas = (long long)grid.x * grid.y;
-    if (ctas < sm_count() && K >= 1024 && (beta == 0.f || beta == 1.f)) {
+    // (transA only: forward / dX products keep a fixed summation order, so duplicate input rows stay bit-identical)
+    if (transA && ctas < sm_count() && K >= 1024 && (beta == 0.f || beta == 1.f)) {
         split = (int)((2LL * sm_count() + ctas - 1) / ctas);
         if (split > K / 256) split = K / 256;
         if (split < 1) split = 1;
