@@ -218,7 +218,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     // ---- column tail or split-K accumulation: direct per-row access
                     if (p.out_dtype == WF_BF16) {
                         __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)                      // static indices: keeps v[] in registers
+                            if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
                     } else {
                         float* dst = static_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
                         if (p.accumulate) {
@@ -226,7 +228,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             for (int j = 0; j < 32; ++j)
                                 if (full || col0 + j < p.N) atomicAdd(dst + j, v[j]);
                         } else {
-                            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = v[j];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) dst[j] = v[j];
                         }
                     }
                 }
