@@ -143,10 +143,17 @@ int wf_enc_l1_bwd(const float* x, const float* W, const float* b, const float* g
  * out_dtype WF_BF16 (store) or WF_F32 (store, or atomic accumulate when accumulate != 0, used with
  * split_k > 1).  rowstats (optional, M*2 floats, ACCUMULATED): per-row sum and sum of squares of
  * the fp32 result incl. bias -- the LayerNorm statistics of models/PointNetEncoder.py:38.
- * Constraints: K % 8 == 0, lda/ldb % 8 == 0 (16-byte TMA strides), pointers 16-byte aligned. */
+ * Constraints: lda/ldb % 8 == 0 (16-byte TMA strides), pointers 16-byte aligned. */
 int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M,
                  int N, int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate,
                  int split_k, float* rowstats, wf_stream_t stream);
+
+/* Same kernel on fp32 storage, multiplied as TF32 (kind::tf32, fp32 accumulate): the heads' Linear layers and their
+ * dX / dW products in production precision.  Mixed operand majorness is allowed (dX = dY * W reads W as stored).
+ * Constraints: lda/ldb/ldd % 4 == 0, pointers 16-byte aligned. */
+int wf_gemm_tf32(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, int M,
+                 int N, int K, const float* bias, float* D, int ldd, int accumulate, int split_k,
+                 wf_stream_t stream);
 
 /* bf16 LayerNorm+ReLU passes between the tensor-core layers (models/PointNetEncoder.py:38-39), 16-byte vectorised,
  * HBM-bound.  fwd: h = relu(LN(z)) with the row statistics from the GEMM epilogue.  bwd: dz from dh and z in ONE pass;

@@ -14,8 +14,12 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def ops():
+    """These tests check the fp32 SIMT kernels: run them in the library's fp32 mode (in production precision big
+    products are routed to TF32 tensor cores, which test_gpu_tc.py covers)."""
     from wf_b200 import ops as o
-    return o
+    o.set_precision("fp32")
+    yield o
+    o.set_precision("bf16")
 
 
 def test_lsap_batched_matches_scipy(ops):

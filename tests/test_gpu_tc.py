@@ -175,3 +175,40 @@ def test_ln_relu_bf16_kernels(ops, C):
     assert_close(dg, gd.grad, 1e-4, "ln bwd dgamma")
     assert_close(dbe, bd.grad, 1e-4, "ln bwd dbeta")
     assert_close(db, zd.grad.sum(0), 2e-3, "ln bwd colsum(dz)")
+
+
+@pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tf32_all_layouts(ops, tA, tB):
+    """wf_gemm_tf32 (tcgen05 kind::tf32 on fp32 storage) in the four operand layouts the heads use, against fp64.
+    TF32 keeps 10 mantissa bits per operand: scale-relative tolerance 2e-3."""
+    from wf_b200._lib import call
+    torch.manual_seed(11)
+    for (M, N, K) in ((64, 4096, 512), (300, 520, 136), (2750, 1536, 512), (61000, 256, 512), (129, 260, 36)):
+        A = torch.randn((K, M) if tA else (M, K), device="cuda")
+        B = torch.randn((N, K) if tB else (K, N), device="cuda") / math.sqrt(K)
+        if A.stride(0) % 4 or B.stride(0) % 4:
+            continue
+        bias = torch.randn(N, device="cuda")
+        ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double()
+        out = torch.full((M, N), float("nan"), device="cuda")
+        call("wf_gemm_tf32", ops._p(A), A.stride(0), int(not tA), ops._p(B), B.stride(0), int(tB), M, N, K, ops._p(bias),
+             ops._p(out), out.stride(0), 0, 1, ops._s())
+        assert_close(out, ref, 2e-3, f"tf32 tA={tA} tB={tB} {M}x{N}x{K}")
+    # split-K accumulate (weight-gradient shape)
+    if tA and not tB:
+        A = torch.randn(61000, 512, device="cuda"); B = torch.randn(61000, 256, device="cuda") / 250
+        out = torch.zeros(512, 256, device="cuda")
+        call("wf_gemm_tf32", ops._p(A), 512, 0, ops._p(B), 256, 0, 512, 256, 61000, None, ops._p(out), 256, 1, 37, ops._s())
+        assert_close(out, A.double().t() @ B.double(), 2e-3, "tf32 split-K dW")
+
+
+def test_heads_tf32_dispatch(ops):
+    """ops.gemm_f32 routes big aligned products to TF32 tensor cores in production precision and to the fp32 SIMT
+    kernel in fp32 mode; both agree within the TF32 tolerance."""
+    torch.manual_seed(12)
+    x = torch.randn(64, 512, device="cuda"); W = torch.randn(4096, 512, device="cuda") / 22
+    ops.set_precision("fp32"); a = ops.gemm_f32(x, W, transB=True)
+    ops.set_precision("bf16"); b = ops.gemm_f32(x, W, transB=True)
+    assert_close(a, x.double() @ W.double().t(), 1e-5, "simt")
+    assert_close(b, a, 2e-3, "tf32 vs simt")
+    assert not torch.equal(a, b)              # i.e. the tensor-core path really ran

@@ -11,7 +11,9 @@
 //   Operand layouts (both through the same 64-element-wide TMA boxes, SWIZZLE_128B):
 //     K-major  : operand stored [rows, K], K contiguous  -> descriptor LBO unused, SBO = 1024 B
 //     MN-major : operand stored [K, rows], rows contiguous (dW = dZ^T * H, reduction over
-//                points) -> one 64x64 box per 64 rows, LBO = 8192 B (next box), SBO = 1024 B
+//                points) -> one (128 B x BK rows) box per 128 B of rows, LBO = box bytes, SBO = 1024 B
+//   Element types: bf16 (kind::f16) for the encoder, tf32 on fp32 storage (kind::tf32, wf_gemm_tf32) for the
+//   heads' fp32 row-MLPs -- same tile geometry in bytes, K per block = 64 resp. 32 elements.
 //
 //   Epilogue (thread = accumulator row): + bias, optional per-row (sum, sumsq) for the following
 //   LayerNorm, then bf16 store, fp32 store or fp32 atomic accumulate (split-K).
@@ -24,11 +26,12 @@
 namespace wf {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_BYTES = BN * BK * 2;          // 32 KB
+// One k-block is 128 bytes of K per row for either element type: 64 bf16 or 32 tf32 (fp32 storage).  All shared-memory
+// byte sizes are therefore identical for both; only element counts differ.
+constexpr int BM = 128, BN = 256, STAGES = 4;
+constexpr int A_BYTES = BM * 128;             // 16 KB
+constexpr int B_BYTES = BN * 128;             // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int BOX_BYTES = 64 * 64 * 2;        // one MN-major box
 constexpr int BAR_BYTES = 256;
 constexpr int STG_LD = 36;                                   // floats per staged row (32 + 4 pad: conflict-free v4 access)
 constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;               // one 32x32 fp32 staging tile per epilogue warp
@@ -45,9 +48,14 @@ struct Params {
     float* rowstats;
 };
 
-template <bool KMAJOR>
+// ESZ = operand element size: 2 -> bf16 (kind::f16), 4 -> tf32 on fp32 storage (kind::tf32).
+// A_KM / B_KM: operand stored K-major ([rows, K]) or MN-major ([K, rows]).
+template <int ESZ, bool A_KM, bool B_KM>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    constexpr int BK = 128 / ESZ;                 // elements of K per k-block
+    constexpr int MNBOX = 128 / ESZ;              // MN-major: rows of the operand per TMA box (128 bytes)
+    constexpr int BOX_BYTES = 128 * BK;           // MN-major box: BK k-rows x 128 bytes
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -90,16 +98,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    if (KMAJOR) {
+                    if (A_KM) {
                         ptx::tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / MNBOX; ++i)
+                            ptx::tma_load_2d(sa + i * BOX_BYTES, &map_a, full_bar(stage), m_blk * BM + i * MNBOX, kb * BK);
+                    }
+                    if (B_KM) {
                         ptx::tma_load_2d(sb, &map_b, full_bar(stage), kb * BK, n_blk * BN);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BM / 64; ++i)
-                            ptx::tma_load_2d(sa + i * BOX_BYTES, &map_a, full_bar(stage), m_blk * BM + i * 64, kb * BK);
-#pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            ptx::tma_load_2d(sb + i * BOX_BYTES, &map_b, full_bar(stage), n_blk * BN + i * 64, kb * BK);
+                        for (int i = 0; i < BN / MNBOX; ++i)
+                            ptx::tma_load_2d(sb + i * BOX_BYTES, &map_b, full_bar(stage), n_blk * BN + i * MNBOX, kb * BK);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -108,9 +119,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN, KMAJOR ? 0 : 1, KMAJOR ? 0 : 1);
-            constexpr uint32_t LBO = KMAJOR ? 16u : (uint32_t)BOX_BYTES;
-            constexpr uint32_t KSTEP = KMAJOR ? 32u : 2048u;     // bytes per UMMA_K=16 along K
+            constexpr uint32_t idesc = ptx::idesc_f32acc(ESZ == 2 ? 1 : 2, BM, BN, A_KM ? 0 : 1, B_KM ? 0 : 1);
+            // one tcgen05.mma consumes 32 bytes of K per row: K-major advances 32 B inside the swizzle row,
+            // MN-major advances (32 / ESZ) k-rows of 128 B
+            constexpr uint32_t LBO_A = A_KM ? 16u : (uint32_t)BOX_BYTES, LBO_B = B_KM ? 16u : (uint32_t)BOX_BYTES;
+            constexpr uint32_t KSTEP_A = A_KM ? 32u : 128u * (32 / ESZ), KSTEP_B = B_KM ? 32u : 128u * (32 / ESZ);
+            // MN-major tf32: swizzle atom is 4 k-rows of 128 B with 32-byte granularity (layout type 1), so the stride
+            // between k-groups is 512 B; all other cases: 8 rows of 128 B (layout type 2), 1024 B
+            constexpr uint32_t LT_A = (ESZ == 4 && !A_KM) ? 1u : 2u, LT_B = (ESZ == 4 && !B_KM) ? 1u : 2u;
+            constexpr uint32_t SBO_A = (ESZ == 4 && !A_KM) ? 512u : 1024u, SBO_B = (ESZ == 4 && !B_KM) ? 512u : 1024u;
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int split = w / (p.tiles_n * p.tiles_m);
@@ -123,10 +140,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     ptx::tc_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = ptx::smem_desc_sw128(sa + k * KSTEP, LBO, 1024u);
-                        const uint64_t db = ptx::smem_desc_sw128(sb + k * KSTEP, LBO, 1024u);
-                        ptx::mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = ptx::smem_desc(sa + k * KSTEP_A, LBO_A, SBO_A, LT_A);
+                        const uint64_t db = ptx::smem_desc(sb + k * KSTEP_B, LBO_B, SBO_B, LT_B);
+                        if (ESZ == 2) ptx::mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else          ptx::mma_tf32_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     ptx::mma_commit(empty_bar(stage));           // frees the smem stage when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -271,17 +289,22 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 tensor map: inner dimension `inner` elements (contiguous), `outer` rows of stride ld elements.
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                    uint32_t box_outer) {
+// 2-D tensor map: inner dimension `inner` elements (contiguous), `outer` rows of stride ld elements.
+// MN-major fp32 (tf32) operands need the 32-byte-atom flavour of the 128-byte swizzle (UMMA SWIZZLE_128B_BASE32B);
+// every other case uses the plain 128-byte swizzle.
+static int make_map(CUtensorMap* m, int esz, bool mn_major, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return WF_ECUDA; }
     cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {ld * 2};
+    cuuint64_t strides[1] = {ld * (uint64_t)esz};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                     const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     (esz == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
                                        (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return WF_ECUDA; }
@@ -291,56 +314,77 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ou
 }  // namespace tc
 }  // namespace wf
 
-extern "C" int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N,
-                            int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k,
-                            float* rowstats, wf_stream_t stream) {
-    using namespace wf;
-    using namespace wf::tc;
-    WF_CHECK_ARG(M > 0 && N > 0 && K > 0, "wf_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
-    WF_CHECK_ARG(a_kmajor == b_kmajor, "wf_gemm_bf16: mixed operand majorness is not built (a=%d b=%d)", a_kmajor, b_kmajor);
-    WF_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "wf_gemm_bf16: lda/ldb must be multiples of 8 (16-byte TMA strides)");
-    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-                 "wf_gemm_bf16: operands must be 16-byte aligned");
-    WF_CHECK_ARG(out_dtype == WF_BF16 || out_dtype == WF_F32, "wf_gemm_bf16: bad out_dtype");
-    WF_CHECK_ARG(!(accumulate && out_dtype != WF_F32), "wf_gemm_bf16: accumulate needs an fp32 output");
-    WF_CHECK_ARG(out_dtype == WF_F32 ? (ldd % 4 == 0) : (ldd % 8 == 0), "wf_gemm_bf16: ldd alignment");
-    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "wf_gemm_bf16: D must be 16-byte aligned");
-    if (split_k < 1) split_k = 1;
-    WF_CHECK_ARG(split_k == 1 || accumulate, "wf_gemm_bf16: split_k > 1 needs accumulate");
+namespace wf { namespace tc {
 
+template <int ESZ, bool A_KM, bool B_KM>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<ESZ, A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    });
+    WF_CUDA(attr_err);
+    gemm_tc_kernel<ESZ, A_KM, B_KM><<<grid, NTHREADS, SMEM_BYTES, s>>>(ma, mb, p);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+// esz 2: bf16 operands; esz 4: fp32 operands multiplied as tf32
+static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N, int K,
+                   const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k, float* rowstats,
+                   cudaStream_t stream) {
+    const int al = 16 / esz;                                     // elements per 16 bytes
+    WF_CHECK_ARG(M > 0 && N > 0 && K > 0, "wf_gemm_tc: empty problem M=%d N=%d K=%d", M, N, K);
+    WF_CHECK_ARG(lda % al == 0 && ldb % al == 0, "wf_gemm_tc: lda/ldb must be multiples of %d elements (16-byte TMA strides)", al);
+    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                 "wf_gemm_tc: operands must be 16-byte aligned");
+    WF_CHECK_ARG(out_dtype == WF_BF16 || out_dtype == WF_F32, "wf_gemm_tc: bad out_dtype");
+    WF_CHECK_ARG(!(accumulate && out_dtype != WF_F32), "wf_gemm_tc: accumulate needs an fp32 output");
+    WF_CHECK_ARG(out_dtype == WF_F32 ? (ldd % 4 == 0) : (ldd % 8 == 0), "wf_gemm_tc: ldd alignment");
+    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "wf_gemm_tc: D must be 16-byte aligned");
+    if (split_k < 1) split_k = 1;
+    WF_CHECK_ARG(split_k == 1 || accumulate, "wf_gemm_tc: split_k > 1 needs accumulate");
+    const int BKe = 128 / esz, mnbox = 128 / esz;
     CUtensorMap ma, mb;
     int rc;
-    if (a_kmajor) {
-        WF_CHECK_ARG(K % 8 == 0, "wf_gemm_bf16: K %% 8 != 0");
-        if ((rc = make_map(&ma, A, K, M, lda, BK, BM)) != WF_OK) return rc;
-        if ((rc = make_map(&mb, B, K, N, ldb, BK, BN)) != WF_OK) return rc;
-    } else {
-        if ((rc = make_map(&ma, A, M, K, lda, 64, 64)) != WF_OK) return rc;
-        if ((rc = make_map(&mb, B, N, K, ldb, 64, 64)) != WF_OK) return rc;
-    }
+    if (a_kmajor) { if ((rc = make_map(&ma, esz, false, A, K, M, lda, BKe, BM)) != WF_OK) return rc; }
+    else          { if ((rc = make_map(&ma, esz, true, A, M, K, lda, mnbox, BKe)) != WF_OK) return rc; }
+    if (b_kmajor) { if ((rc = make_map(&mb, esz, false, B, K, N, ldb, BKe, BN)) != WF_OK) return rc; }
+    else          { if ((rc = make_map(&mb, esz, true, B, N, K, ldb, mnbox, BKe)) != WF_OK) return rc; }
     Params p;
     p.M = M; p.N = N; p.K = K;
     p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
-    p.nkb = cdiv(K, BK);
+    p.nkb = cdiv(K, BKe);
     if (split_k > p.nkb) split_k = p.nkb;
     p.kb_per_split = cdiv(p.nkb, split_k);
     p.split_k = cdiv(p.nkb, p.kb_per_split);
     p.bias = bias; p.D = D; p.ldd = ldd; p.out_dtype = out_dtype; p.accumulate = accumulate; p.rowstats = rowstats;
     const long long items = (long long)p.tiles_m * p.tiles_n * p.split_k;
     const int grid = (int)(items < sm_count() ? items : sm_count());
+    const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
+    switch (key) {
+        case 3: return launch<2, true, true>(ma, mb, p, grid, stream);
+        case 2: return launch<2, true, false>(ma, mb, p, grid, stream);
+        case 1: return launch<2, false, true>(ma, mb, p, grid, stream);
+        case 0: return launch<2, false, false>(ma, mb, p, grid, stream);
+        case 7: return launch<4, true, true>(ma, mb, p, grid, stream);
+        case 6: return launch<4, true, false>(ma, mb, p, grid, stream);
+        case 5: return launch<4, false, true>(ma, mb, p, grid, stream);
+        default: return launch<4, false, false>(ma, mb, p, grid, stream);
+    }
+}
 
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    });
-    WF_CUDA(attr_err);
-    if (a_kmajor)
-        gemm_bf16_kernel<true><<<grid, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(ma, mb, p);
-    else
-        gemm_bf16_kernel<false><<<grid, NTHREADS, SMEM_BYTES, as_stream(stream)>>>(ma, mb, p);
-    WF_LAUNCH_CHECK();
-    return WF_OK;
+}}  // namespace wf::tc
+
+extern "C" int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N,
+                            int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k,
+                            float* rowstats, wf_stream_t stream) {
+    return wf::tc::gemm_tc(2, A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias, D, ldd, out_dtype, accumulate, split_k,
+                           rowstats, wf::as_stream(stream));
+}
+
+extern "C" int wf_gemm_tf32(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, int M, int N,
+                            int K, const float* bias, float* D, int ldd, int accumulate, int split_k, wf_stream_t stream) {
+    return wf::tc::gemm_tc(4, A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias, D, ldd, WF_F32, accumulate, split_k,
+                           nullptr, wf::as_stream(stream));
 }

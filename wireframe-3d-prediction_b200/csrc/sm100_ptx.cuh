@@ -95,6 +95,14 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -115,24 +123,24 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "memory");
 }
 
-// Shared-memory matrix descriptor (tcgen05 "SmemDescriptor"): 128-byte swizzle, sm_100 version bit.
+// Shared-memory matrix descriptor (tcgen05 "SmemDescriptor"), sm_100 version bit.
 //   bits [0,14) start address >> 4 | [16,30) leading-dim byte offset >> 4 | [32,46) stride byte offset >> 4
-//   bits [46,48) = 1 (Blackwell) | [61,64) = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   bits [46,48) = 1 (Blackwell) | [61,64) layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
-//   [4,6) D format 1=f32 | [7,10) A format 1=bf16 | [10,13) B format 1=bf16
+// Instruction descriptor for kind::f16 / kind::tf32 with fp32 D.  fmt: 1 = bf16, 2 = tf32 (A and B alike).
+//   [4,6) D format 1=f32 | [7,10) A format | [10,13) B format
 //   [15] A major (0=K, 1=MN) | [16] B major | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t idesc_f32acc(int fmt, int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
            (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
 }

@@ -30,6 +30,16 @@ def get_precision() -> str:
     return _PRECISION
 
 
+_SMS = {}
+
+
+def _sm_count() -> int:
+    d = torch.cuda.current_device()
+    if d not in _SMS:
+        _SMS[d] = torch.cuda.get_device_properties(d).multi_processor_count
+    return _SMS[d]
+
+
 LAUNCHES = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
@@ -71,13 +81,44 @@ def _rowmajor(t: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # raw kernels (no autograd)
 # ----------------------------------------------------------------------------------------------
+USE_TF32_HEADS = os.environ.get("WF_B200_TF32_HEADS", "1") == "1"
+_TC_MIN_MACS = 1 << 22
+
+
+def _tc_operand_ok(t: torch.Tensor) -> bool:
+    return (t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0)
+
+
 def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0, bias=None):
+    """C = alpha * op(A) op(B) + beta * C (+ bias), fp32 storage.
+    Production precision ('bf16' mode): large, 16-byte-aligned products run on the tensor cores as TF32
+    (wf_gemm_tf32, tcgen05 kind::tf32, fp32 accumulate); everything else, and the whole 'fp32' parity mode,
+    runs on the fp32 SIMT kernel (wf_gemm_f32)."""
     A, B = _rowmajor(A), _rowmajor(B)
     M, K = (A.shape[1], A.shape[0]) if transA else A.shape
     N = B.shape[0] if transB else B.shape[1]
     kb = B.shape[1] if transB else B.shape[0]
     if kb != K:
         raise ValueError(f"gemm shape mismatch {tuple(A.shape)} {tuple(B.shape)} tA={transA} tB={transB}")
+    if (_PRECISION == "bf16" and USE_TF32_HEADS and alpha == 1.0 and beta in (0.0, 1.0) and M * N * K >= _TC_MIN_MACS
+            and _tc_operand_ok(A) and _tc_operand_ok(B) and (out is None or _tc_operand_ok(out))
+            and (bias is None or bias.data_ptr() % 16 == 0)):
+        tiles = ((M + 127) // 128) * ((N + 255) // 256)
+        split = 1
+        if transA and bias is None and K >= 1024:
+            sms = _sm_count()
+            if tiles < sms:
+                split = max(1, min((2 * sms + tiles - 1) // tiles, K // 128))
+        accumulate = split > 1 or (out is not None and beta == 1.0)
+        if out is None:
+            out = (torch.zeros if accumulate else torch.empty)(M, N, device=A.device, dtype=torch.float32)
+        elif beta == 0.0 and accumulate:
+            out.zero_()
+        call("wf_gemm_tf32", _p(A), A.stride(0), int(not transA), _p(B), B.stride(0), int(transB), M, N, K, _p(bias),
+             _p(out), out.stride(0), int(accumulate), int(split), _s())
+        _count()
+        return out
     if out is None:
         out = torch.empty(M, N, device=A.device, dtype=torch.float32)
         beta = 0.0
@@ -287,10 +328,6 @@ def cast_bf16(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     call("wf_cast_bf16", _p(w), R, C, _p(out), int(transpose), _s())
     _count()
     return out
-
-
-def _sm_count() -> int:
-    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 
 
 class EncoderPointMLP_TC(torch.autograd.Function):
