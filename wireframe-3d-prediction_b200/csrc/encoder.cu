@@ -296,6 +296,42 @@ __global__ void pool_bwd_kernel(const float* __restrict__ g_max_m, const float* 
     }
 }
 
+// bf16 variant: thread owns 8 consecutive channels (one 16-byte store per point), per-channel terms live in registers
+__global__ void __launch_bounds__(256)
+pool_bwd_bf16_kernel(const float* __restrict__ g_max_m, const float* __restrict__ g_avg_m, const float* __restrict__ g_max_u,
+                     const float* __restrict__ g_mean_u, const int* __restrict__ arg_m, const int* __restrict__ arg_u,
+                     const uint8_t* __restrict__ mask, const float* __restrict__ valid, int N, int C, uint4* __restrict__ d_pf) {
+    const int b = blockIdx.z;
+    const int c0 = threadIdx.x * 8;
+    const float invN = 1.0f / (float)N, inv_valid = 1.0f / valid[b];
+    float ga[8], gu[8], gm[8], gx[8];
+    int am[8], au[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const size_t o = (size_t)b * C + c0 + i;
+        ga[i] = g_avg_m ? g_avg_m[o] * inv_valid : 0.f;
+        gu[i] = g_mean_u ? g_mean_u[o] * invN : 0.f;
+        gm[i] = g_max_m ? g_max_m[o] : 0.f; gx[i] = g_max_u ? g_max_u[o] : 0.f;
+        am[i] = g_max_m ? arg_m[o] : -1; au[i] = g_max_u ? arg_u[o] : -1;
+    }
+    const int C8 = C >> 3;
+    for (int n = blockIdx.y * blockDim.y + threadIdx.y; n < N; n += gridDim.y * blockDim.y) {
+        const bool mk = mask[(size_t)b * N + n] != 0;
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            float v0 = gu[i] + (mk ? ga[i] : 0.f), v1 = gu[i + 1] + (mk ? ga[i + 1] : 0.f);
+            if (am[i] == n) v0 += gm[i];
+            if (au[i] == n) v0 += gx[i];
+            if (am[i + 1] == n) v1 += gm[i + 1];
+            if (au[i + 1] == n) v1 += gx[i + 1];
+            h[i >> 1] = __floats2bfloat162_rn(v0, v1);
+        }
+        d_pf[((size_t)b * N + n) * C8 + threadIdx.x] = u;
+    }
+}
+
 }  // namespace enc
 }  // namespace wf
 
@@ -376,6 +412,15 @@ extern "C" int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const flo
     using namespace wf;
     if (B <= 0 || N <= 0 || C <= 0) return WF_OK;
     WF_CHECK_ARG(B <= 65535, "wf_pool_bwd: B > 65535");
+    if (d_dtype == WF_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && (reinterpret_cast<uintptr_t>(d_pf) & 15) == 0) {
+        dim3 block(C / 8, 256 / (C / 8));
+        const int want = cdiv(N, (int)block.y);
+        dim3 g2(1, want < 64 ? want : 64, B);
+        enc::pool_bwd_bf16_kernel<<<g2, block, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid,
+                                                                   N, C, static_cast<uint4*>(d_pf));
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
     dim3 grid(cdiv(C, 256), N < 16384 ? N : 16384, B);
     if (d_dtype == WF_F32) enc::pool_bwd_kernel<WF_F32><<<grid, 256, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid, N, C, d_pf);
     else if (d_dtype == WF_BF16) enc::pool_bwd_kernel<WF_BF16><<<grid, 256, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid, N, C, d_pf);

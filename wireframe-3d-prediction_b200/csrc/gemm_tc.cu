@@ -22,6 +22,7 @@
 
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace wf {
 namespace tc {
@@ -42,6 +43,7 @@ constexpr int NTHREADS = 256;
 struct Params {
     int M, N, K;
     int tiles_m, tiles_n, split_k, kb_per_split, nkb;
+    int streamk;                 // accumulate mode: balance (tile, k-block) units evenly over the workers
     const float* bias;
     void* D;
     int ldd, out_dtype, accumulate;
@@ -50,7 +52,46 @@ struct Params {
 
 // ESZ = operand element size: 2 -> bf16 (kind::f16), 4 -> tf32 on fp32 storage (kind::tf32).
 // A_KM / B_KM: operand stored K-major ([rows, K]) or MN-major ([K, rows]).
-template <int ESZ, bool A_KM, bool B_KM>
+// MC: CTAs run as clusters of 2 that work on the same N tile and adjacent M tiles in lock step; each CTA fetches half
+//     of the shared B tile and TMA-multicasts it into both CTAs' shared memory (L2 -> SM traffic for B halves;
+//     the kernel is L2-bandwidth-bound at 128x256 tiles otherwise).  MMAs stay cta_group::1.
+// Work distribution, evaluated identically by the producer, MMA and epilogue roles.
+//   classic : item w -> (tile, split); items are dealt round-robin to the workers (a worker = CTA, or cluster when MC)
+//   stream-K: the (tile, k-block) space is cut into one contiguous, equally long range per worker; a range may end
+//             inside a tile (its partial sum is added atomically), so the weight-gradient GEMMs -- few output tiles,
+//             very long K -- keep every SM busy without wave quantisation.
+struct Sched {
+    int tiles_n, m_units, nkb, kb_per_split, n_items, w, w_step, streamk;
+    long long u, u_end;
+    __device__ __forceinline__ Sched(const Params& p, int m_units_, int worker, int n_workers)
+        : tiles_n(p.tiles_n), m_units(m_units_), nkb(p.nkb), kb_per_split(p.kb_per_split),
+          n_items(m_units_ * p.tiles_n * p.split_k), w(worker), w_step(n_workers), streamk(p.streamk) {
+        const long long total = (long long)m_units_ * p.tiles_n * p.nkb;
+        const long long per = (total + n_workers - 1) / n_workers;
+        u = (long long)worker * per;
+        u_end = u + per < total ? u + per : total;
+    }
+    __device__ __forceinline__ bool next(int& n_blk, int& mu, int& kb0, int& kb1) {
+        if (streamk) {
+            if (u >= u_end) return false;
+            const long long tile = u / nkb;
+            kb0 = (int)(u - tile * nkb);
+            const long long take = (long long)(nkb - kb0) < u_end - u ? (long long)(nkb - kb0) : u_end - u;
+            kb1 = kb0 + (int)take;
+            u += take;
+            n_blk = (int)(tile % tiles_n); mu = (int)(tile / tiles_n);
+            return true;
+        }
+        if (w >= n_items) return false;
+        n_blk = w % tiles_n; mu = (w / tiles_n) % m_units;
+        const int split = w / (tiles_n * m_units);
+        kb0 = split * kb_per_split; kb1 = min(nkb, kb0 + kb_per_split);
+        w += w_step;
+        return true;
+    }
+};
+
+template <int ESZ, bool A_KM, bool B_KM, bool MC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
     constexpr int BK = 128 / ESZ;                 // elements of K per k-block
@@ -67,14 +108,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));   // inside BAR_BYTES
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = p.tiles_m * p.tiles_n * p.split_k;
+    // work items: MC -> one item per CLUSTER covers two adjacent M tiles (this CTA takes 2*pair + rank)
+    const int crank = MC ? (int)ptx::cluster_ctarank() : 0;
+    const int m_units = MC ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), MC ? 2 : 1); }
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
         ptx::fence_barrier_init();
     }
@@ -84,6 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (MC) ptx::cluster_sync();                 // peer barriers are initialised before any multicast / remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -91,9 +137,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-                const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m, split = w / (p.tiles_n * p.tiles_m);
-                const int kb0 = split * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+            Sched sched(p, m_units, w_first, w_step);
+            int n_blk, mu, kb0, kb1;
+            while (sched.next(n_blk, mu, kb0, kb1)) {
+                const int m_blk = MC ? 2 * mu + crank : mu;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -105,12 +152,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int i = 0; i < BM / MNBOX; ++i)
                             ptx::tma_load_2d(sa + i * BOX_BYTES, &map_a, full_bar(stage), m_blk * BM + i * MNBOX, kb * BK);
                     }
-                    if (B_KM) {
-                        ptx::tma_load_2d(sb, &map_b, full_bar(stage), kb * BK, n_blk * BN);
-                    } else {
+                    if (!MC) {
+                        if (B_KM) {
+                            ptx::tma_load_2d(sb, &map_b, full_bar(stage), kb * BK, n_blk * BN);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < BN / MNBOX; ++i)
-                            ptx::tma_load_2d(sb + i * BOX_BYTES, &map_b, full_bar(stage), n_blk * BN + i * MNBOX, kb * BK);
+                            for (int i = 0; i < BN / MNBOX; ++i)
+                                ptx::tma_load_2d(sb + i * BOX_BYTES, &map_b, full_bar(stage), n_blk * BN + i * MNBOX, kb * BK);
+                        }
+                    } else {
+                        // this CTA's half of the B tile, delivered to both CTAs (same smem offset, same barrier offset)
+                        if (B_KM) {
+                            ptx::tma_load_2d_mc(sb + crank * (B_BYTES / 2), &map_b, full_bar(stage), kb * BK,
+                                                n_blk * BN + crank * (BN / 2), 3);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / MNBOX / 2; ++i) {
+                                const int bi = crank * (BN / MNBOX / 2) + i;
+                                ptx::tma_load_2d_mc(sb + bi * BOX_BYTES, &map_b, full_bar(stage), n_blk * BN + bi * MNBOX, kb * BK, 3);
+                            }
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -129,9 +190,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             constexpr uint32_t LT_A = (ESZ == 4 && !A_KM) ? 1u : 2u, LT_B = (ESZ == 4 && !B_KM) ? 1u : 2u;
             constexpr uint32_t SBO_A = (ESZ == 4 && !A_KM) ? 512u : 1024u, SBO_B = (ESZ == 4 && !B_KM) ? 512u : 1024u;
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-                const int split = w / (p.tiles_n * p.tiles_m);
-                const int kb0 = split * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+            Sched sched(p, m_units, w_first, w_step);
+            int n_blk, mu, kb0, kb1;
+            while (sched.next(n_blk, mu, kb0, kb1)) {
                 ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
@@ -146,7 +207,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (ESZ == 2) ptx::mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         else          ptx::mma_tf32_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    ptx::mma_commit(empty_bar(stage));           // frees the smem stage when the MMAs retire
+                    // frees the smem stage when the MMAs retire (MC: in both CTAs -- the peer multicasts into our stage)
+                    if (MC) ptx::mma_commit_mc(empty_bar(stage), 3); else ptx::mma_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 ptx::mma_commit(tfull_bar(acc));                 // accumulator ready for the epilogue
@@ -162,8 +224,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + q * 32 * STG_LD;
         const bool bias_v4 = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-            const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m;
+        Sched sched(p, m_units, w_first, w_step);
+        int n_blk, mu, kb0, kb1;
+        while (sched.next(n_blk, mu, kb0, kb1)) {
+            const int m_blk = MC ? 2 * mu + crank : mu;
             const int row0 = m_blk * BM + q * 32;
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
@@ -266,6 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (MC) ptx::cluster_sync();                 // nobody exits while the peer may still write our smem / barriers
     if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -316,17 +381,33 @@ static int make_map(CUtensorMap* m, int esz, bool mn_major, const void* ptr, uin
 
 namespace wf { namespace tc {
 
-template <int ESZ, bool A_KM, bool B_KM>
+template <int ESZ, bool A_KM, bool B_KM, bool MC>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<ESZ, A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<ESZ, A_KM, B_KM, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     WF_CUDA(attr_err);
-    gemm_tc_kernel<ESZ, A_KM, B_KM><<<grid, NTHREADS, SMEM_BYTES, s>>>(ma, mb, p);
-    WF_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = MC ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    WF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<ESZ, A_KM, B_KM, MC>, ma, mb, p));
     return WF_OK;
+}
+
+template <int ESZ, bool A_KM, bool B_KM>
+static int launch_mc(bool mc, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
+    return mc ? launch<ESZ, A_KM, B_KM, true>(ma, mb, p, grid, s) : launch<ESZ, A_KM, B_KM, false>(ma, mb, p, grid, s);
+}
+
+static bool cluster_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("WF_B200_GEMM_CLUSTER"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 
 // esz 2: bf16 operands; esz 4: fp32 operands multiplied as tf32
@@ -349,28 +430,52 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     int rc;
     if (a_kmajor) { if ((rc = make_map(&ma, esz, false, A, K, M, lda, BKe, BM)) != WF_OK) return rc; }
     else          { if ((rc = make_map(&ma, esz, true, A, M, K, lda, mnbox, BKe)) != WF_OK) return rc; }
-    if (b_kmajor) { if ((rc = make_map(&mb, esz, false, B, K, N, ldb, BKe, BN)) != WF_OK) return rc; }
+    // multicast pairs pay off when there are at least two M tiles to pair up
+    const bool mc = cluster_enabled() && cdiv(M, BM) >= 2 && sm_count() >= 2;
+    if (b_kmajor) { if ((rc = make_map(&mb, esz, false, B, K, N, ldb, BKe, mc ? BN / 2 : BN)) != WF_OK) return rc; }
     else          { if ((rc = make_map(&mb, esz, true, B, N, K, ldb, mnbox, BKe)) != WF_OK) return rc; }
     Params p;
     p.M = M; p.N = N; p.K = K;
     p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
     p.nkb = cdiv(K, BKe);
+    const int m_units = mc ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int workers_max = mc ? sm_count() / 2 : sm_count();
+    static const bool streamk_env = [] { const char* e = getenv("WF_B200_GEMM_STREAMK"); return e && e[0] == '1'; }();
+    p.streamk = (streamk_env && accumulate && split_k > 1 && bias == nullptr && rowstats == nullptr) ? 1 : 0;
+    if (split_k > 1 && !p.streamk) {
+        // The caller's split_k is a hint ("reduction-heavy").  Items are dealt round-robin, split index slowest, so the
+        // CTAs running together read the same K range of both operands (L2 reuse); pick the smallest split whose
+        // item count fills whole waves of workers (>= 95 %), which is what removes the wave-quantisation loss.
+        const long long tiles = (long long)m_units * p.tiles_n;
+        int best = 1; double best_eff = 0.0;
+        const int smax = p.nkb / 8 < 64 ? (p.nkb / 8 < 1 ? 1 : p.nkb / 8) : 64;
+        for (int sp = 1; sp <= smax; ++sp) {
+            const long long it = tiles * sp;
+            const long long waves = (it + workers_max - 1) / workers_max;
+            const double eff = (double)it / (double)(waves * workers_max);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+            if (eff >= 0.95) { best = sp; break; }
+        }
+        split_k = best;
+    }
     if (split_k > p.nkb) split_k = p.nkb;
     p.kb_per_split = cdiv(p.nkb, split_k);
     p.split_k = cdiv(p.nkb, p.kb_per_split);
     p.bias = bias; p.D = D; p.ldd = ldd; p.out_dtype = out_dtype; p.accumulate = accumulate; p.rowstats = rowstats;
-    const long long items = (long long)p.tiles_m * p.tiles_n * p.split_k;
-    const int grid = (int)(items < sm_count() ? items : sm_count());
+    long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
+                                : (long long)m_units * p.tiles_n * p.split_k;
+    const int workers = (int)(items < workers_max ? items : workers_max);
+    const int grid = mc ? 2 * workers : workers;
     const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
     switch (key) {
-        case 3: return launch<2, true, true>(ma, mb, p, grid, stream);
-        case 2: return launch<2, true, false>(ma, mb, p, grid, stream);
-        case 1: return launch<2, false, true>(ma, mb, p, grid, stream);
-        case 0: return launch<2, false, false>(ma, mb, p, grid, stream);
-        case 7: return launch<4, true, true>(ma, mb, p, grid, stream);
-        case 6: return launch<4, true, false>(ma, mb, p, grid, stream);
-        case 5: return launch<4, false, true>(ma, mb, p, grid, stream);
-        default: return launch<4, false, false>(ma, mb, p, grid, stream);
+        case 3: return launch_mc<2, true, true>(mc, ma, mb, p, grid, stream);
+        case 2: return launch_mc<2, true, false>(mc, ma, mb, p, grid, stream);
+        case 1: return launch_mc<2, false, true>(mc, ma, mb, p, grid, stream);
+        case 0: return launch_mc<2, false, false>(mc, ma, mb, p, grid, stream);
+        case 7: return launch_mc<4, true, true>(mc, ma, mb, p, grid, stream);
+        case 6: return launch_mc<4, true, false>(mc, ma, mb, p, grid, stream);
+        case 5: return launch_mc<4, false, true>(mc, ma, mb, p, grid, stream);
+        default: return launch_mc<4, false, false>(mc, ma, mb, p, grid, stream);
     }
 }
 
