@@ -31,6 +31,9 @@ for p in (PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# NCCL prints its version banner to STDOUT when NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line.
+os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 POINTS, VERTS, PER_GPU_BATCH, FEATS = 10000, 64, 64, 8
@@ -62,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -314,7 +317,7 @@ def make_counts_only(rank, B):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="wf_b200", choices=["wf_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
