@@ -176,11 +176,13 @@ int wf_cast_bf16(const float* src, int R, int C, void* dst, int transpose, wf_st
 int wf_pool_fwd(const float* pf, const uint8_t* mask, const float* valid, int B, int N, int C,
                 float* max_m, int32_t* arg_m, float* avg_m, float* max_u, int32_t* arg_u,
                 float* mean_u, wf_stream_t stream);
-/* Backward: d_pf[b,n,c] = mask*g_avg/valid + g_mean/N + [n==arg_m]*g_max_m*finite + [n==arg_u]*g_max_u */
+/* Backward: d_pf[b,n,c] = mask*g_avg/valid + g_mean/N + [n==arg_m]*g_max_m*finite + [n==arg_u]*g_max_u.
+ * dbias (optional, C floats, accumulated; bf16 output only) = sum over all points of d_pf in closed form: the bias
+ * gradient of the Linear that produced the point features. */
 int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u,
                 const float* g_mean_u, const int32_t* arg_m, const int32_t* arg_u,
                 const uint8_t* mask, const float* valid, int B, int N, int C, void* d_pf,
-                int d_dtype, wf_stream_t stream);
+                int d_dtype, float* dbias, wf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Edge head: ragged batch, vertices of all samples concatenated,

@@ -300,7 +300,8 @@ __global__ void pool_bwd_kernel(const float* __restrict__ g_max_m, const float* 
 __global__ void __launch_bounds__(256)
 pool_bwd_bf16_kernel(const float* __restrict__ g_max_m, const float* __restrict__ g_avg_m, const float* __restrict__ g_max_u,
                      const float* __restrict__ g_mean_u, const int* __restrict__ arg_m, const int* __restrict__ arg_u,
-                     const uint8_t* __restrict__ mask, const float* __restrict__ valid, int N, int C, uint4* __restrict__ d_pf) {
+                     const uint8_t* __restrict__ mask, const float* __restrict__ valid, int N, int C, uint4* __restrict__ d_pf,
+                     float* __restrict__ dbias) {
     const int b = blockIdx.z;
     const int c0 = threadIdx.x * 8;
     const float invN = 1.0f / (float)N, inv_valid = 1.0f / valid[b];
@@ -313,6 +314,17 @@ pool_bwd_bf16_kernel(const float* __restrict__ g_max_m, const float* __restrict_
         gu[i] = g_mean_u ? g_mean_u[o] * invN : 0.f;
         gm[i] = g_max_m ? g_max_m[o] : 0.f; gx[i] = g_max_u ? g_max_u[o] : 0.f;
         am[i] = g_max_m ? arg_m[o] : -1; au[i] = g_max_u ? arg_u[o] : -1;
+    }
+    // bias gradient of the final Linear = sum over points of d_pf, in closed form from the pooled gradients
+    // (mean terms sum back to the pooled gradient, each max term lands on exactly one point)
+    if (dbias != nullptr && blockIdx.y == 0 && threadIdx.y == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = gu[i] * (float)N;
+            if (am[i] >= 0) t += ga[i] * valid[b] + gm[i];      // am < 0 <=> no valid point in this cloud: masked terms vanish
+            if (au[i] >= 0) t += gx[i];
+            atomicAdd(dbias + c0 + i, t);
+        }
     }
     const int C8 = C >> 3;
     for (int n = blockIdx.y * blockDim.y + threadIdx.y; n < N; n += gridDim.y * blockDim.y) {
@@ -408,7 +420,7 @@ extern "C" int wf_pool_fwd(const float* pf, const uint8_t* mask, const float* va
 
 extern "C" int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u, const float* g_mean_u,
                            const int32_t* arg_m, const int32_t* arg_u, const uint8_t* mask, const float* valid, int B, int N,
-                           int C, void* d_pf, int d_dtype, wf_stream_t stream) {
+                           int C, void* d_pf, int d_dtype, float* dbias, wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || N <= 0 || C <= 0) return WF_OK;
     WF_CHECK_ARG(B <= 65535, "wf_pool_bwd: B > 65535");
@@ -417,10 +429,11 @@ extern "C" int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const flo
         const int want = cdiv(N, (int)block.y);
         dim3 g2(1, want < 64 ? want : 64, B);
         enc::pool_bwd_bf16_kernel<<<g2, block, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid,
-                                                                   N, C, static_cast<uint4*>(d_pf));
+                                                                   N, C, static_cast<uint4*>(d_pf), dbias);
         WF_LAUNCH_CHECK();
         return WF_OK;
     }
+    WF_CHECK_ARG(dbias == nullptr, "wf_pool_bwd: dbias is only produced by the bf16 vector kernel (C %% 8 == 0, C <= 2048)");
     dim3 grid(cdiv(C, 256), N < 16384 ? N : 16384, B);
     if (d_dtype == WF_F32) enc::pool_bwd_kernel<WF_F32><<<grid, 256, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid, N, C, d_pf);
     else if (d_dtype == WF_BF16) enc::pool_bwd_kernel<WF_BF16><<<grid, 256, 0, as_stream(stream)>>>(g_max_m, g_avg_m, g_max_u, g_mean_u, arg_m, arg_u, mask, valid, N, C, d_pf);

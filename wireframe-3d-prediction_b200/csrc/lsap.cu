@@ -158,6 +158,139 @@ __device__ int solve_warp(const Work& w, int nr, int nc, int lane) {
     return WF_LSAP_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-resident variant for nc <= 32*CPL: lane l owns columns l, l+32, ... and keeps their dual
+// variable v, tentative distance, pool slot and owner row in registers; the Dijkstra step is then one
+// shared-memory read of the cost entry, three fp64 adds and six REDUX warp reductions -- no pool array,
+// no second pass over shared memory.  Semantics (incl. scipy's tie rules) identical to solve_warp:
+// the pool is implicit -- slot[j] is column j's position in scipy's `remaining` array, seeded as
+// nc-1-j, and "move the last entry into the freed slot" becomes "the column at slot live-1 takes slot s".
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f64_key(double d) {        // order-preserving map to u64
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ double warp_min_f64_redux(double x) {
+    const unsigned long long k = f64_key(x);
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return key_f64(((unsigned long long)mh << 32) | ml);
+}
+
+template <int CPL>
+__device__ int solve_warp_reg(const Work& w, int nr, int nc, int lane) {
+    int bad = 0;
+    for (int k = lane; k < nr * nc; k += 32) {
+        const float c = w.cost[k];
+        bad |= (c != c) || (c == -CUDART_INF_F);
+    }
+    if (__any_sync(0xffffffffu, bad)) return WF_LSAP_INVALID;
+    for (int i = lane; i < nr; i += 32) { w.u[i] = 0.0; w.col_of_row[i] = -1; }
+    for (int j = lane; j < nc; j += 32) { w.row_of_col[j] = -1; w.pred[j] = -1; }
+    double v[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) v[k] = 0.0;
+    __syncwarp();
+
+    for (int cur = 0; cur < nr; ++cur) {
+        double dist[CPL];
+        int slot[CPL], rowof[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int j = lane + 32 * k;
+            dist[k] = CUDART_INF;
+            slot[k] = j < nc ? nc - 1 - j : -2;              // -2: column does not exist, -1: scanned
+            rowof[k] = j < nc ? w.row_of_col[j] : 0;
+        }
+        for (int i = lane; i < nr; i += 32) w.row_seen[i] = 0;
+        __syncwarp();
+        int live = nc, sink = -1, row = cur;
+        double frontier = 0.0;
+        while (sink < 0) {
+            if (lane == 0) w.row_seen[row] = 1;
+            const double u_row = w.u[row];
+            const float* crow = w.cost + (size_t)row * nc;
+            double lmin = CUDART_INF;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                if (slot[k] >= 0) {
+                    const int j = lane + 32 * k;
+                    const double cand = ((frontier + (double)crow[j]) - u_row) - v[k];
+                    if (cand < dist[k]) { dist[k] = cand; w.pred[j] = row; }
+                    lmin = dist[k] < lmin ? dist[k] : lmin;
+                }
+            }
+            const double m = warp_min_f64_redux(lmin);
+            if (m == CUDART_INF) return WF_LSAP_INFEASIBLE;
+            int first = 0x7fffffff, ulast = -1;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                if (slot[k] >= 0 && dist[k] == m) {
+                    first = min(first, slot[k]);
+                    if (rowof[k] < 0) ulast = max(ulast, slot[k]);
+                }
+            }
+            const int s1 = __reduce_min_sync(0xffffffffu, first);
+            const int ubest = __reduce_max_sync(0xffffffffu, ulast == s1 ? -1 : ulast);
+            const int s = ubest >= 0 ? ubest : s1;
+            int mine_j = -1, mine_owner = -1;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k)
+                if (slot[k] == s) { mine_j = lane + 32 * k; mine_owner = rowof[k] + 1; }
+            const int jsel = __reduce_max_sync(0xffffffffu, mine_j);
+            const int owner = __reduce_max_sync(0xffffffffu, mine_owner) - 1;     // -1 -> unassigned column
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                if (slot[k] == s) slot[k] = -1;                   // scanned
+                else if (slot[k] == live - 1) slot[k] = s;        // the pool's last entry moves into the hole
+            }
+            --live;
+            frontier = m;
+            if (owner < 0) sink = jsel; else row = owner;
+        }
+        // publish the distances of scanned columns, then the dual update
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int j = lane + 32 * k;
+            if (j < nc) w.dist[j] = dist[k];
+        }
+        __syncwarp();
+        for (int i = lane; i < nr; i += 32) {
+            if (i == cur) w.u[i] = w.u[i] + frontier;
+            else if (w.row_seen[i]) w.u[i] = w.u[i] + (frontier - w.dist[w.col_of_row[i]]);
+        }
+#pragma unroll
+        for (int k = 0; k < CPL; ++k)
+            if (slot[k] == -1) v[k] = v[k] - (frontier - dist[k]);
+        __syncwarp();
+        if (lane == 0) {
+            int j = sink;
+            while (true) {
+                const int i = w.pred[j];
+                const int prev = w.col_of_row[i];
+                w.row_of_col[j] = i;
+                w.col_of_row[i] = j;
+                j = prev;
+                if (i == cur) break;
+            }
+        }
+        __syncwarp();
+    }
+    return WF_LSAP_OK;
+}
+
+__device__ __forceinline__ int solve_any(const Work& w, int nr, int nc, int lane) {
+    if (nc <= 32) return solve_warp_reg<1>(w, nr, nc, lane);
+    if (nc <= 64) return solve_warp_reg<2>(w, nr, nc, lane);
+    if (nc <= 128) return solve_warp_reg<4>(w, nr, nc, lane);
+    return solve_warp(w, nr, nc, lane);
+}
+
 constexpr int WARPS_PER_CTA = 4;
 
 // Generic: raw float32 matrices from global memory.
@@ -182,7 +315,7 @@ __global__ void lsap_batched_kernel(const float* __restrict__ cost, long long ba
         if (flip) w.cost[(size_t)j * nc + i] = c; else w.cost[(size_t)i * nc + j] = c;
     }
     __syncwarp();
-    const int st = solve_warp(w, nr, nc, lane);
+    const int st = solve_any(w, nr, nc, lane);
     if (lane == 0) status[b] = st;
     if (st != WF_LSAP_OK) return;
     __syncwarp();
@@ -224,7 +357,7 @@ __global__ void loss_match_kernel(const float* __restrict__ pred_v, const float*
         if (cost_dump) cost_dump[(size_t)b * V * V + k] = c;
     }
     __syncwarp();
-    const int st = solve_warp(w, V, V, lane);
+    const int st = solve_any(w, V, V, lane);
     if (lane == 0) status[b] = st;
     if (st != WF_LSAP_OK) return;
     __syncwarp();

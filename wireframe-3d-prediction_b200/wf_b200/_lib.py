@@ -45,7 +45,7 @@ SIGNATURES = {
     "wf_stats_finalize": [P, I, I, F, P, P, P],
     "wf_cast_bf16": [P, I, I, P, I, P],
     "wf_pool_fwd": [P, P, P, I, I, I, P, P, P, P, P, P, P],
-    "wf_pool_bwd": [P, P, P, P, P, P, P, P, I, I, I, P, I, P],
+    "wf_pool_bwd": [P, P, P, P, P, P, P, P, I, I, I, P, I, P, P],
     "wf_gather_prefix": [P, I, I, P, I, P, P],
     "wf_scatter_prefix_add": [P, I, I, P, I, P, P],
     "wf_attn_fwd": [P, P, P, I, I, I, I, P, P, P, F, P],

@@ -294,7 +294,7 @@ class PoolPoints(torch.autograd.Function):
         # temporary would dangle once the caching allocator hands the block to the next temporary
         gs = [None if g is None else _f32c(g) for g in (g_max_m, g_avg_m, g_max_u, g_mean_u)]
         call("wf_pool_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u),
-             _p(mask), _p(valid), B, N, C, _p(d_pf), F32, _s())
+             _p(mask), _p(valid), B, N, C, _p(d_pf), F32, None, _s())
         _count()
         return d_pf, None, None
 
@@ -390,11 +390,13 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         gs = [None if g is None else _f32c(g) for g in (g_max_m, g_avg_m, g_max_u, g_mean_u)]   # held until the launch
         C5 = W5.shape[0]
         dz = torch.empty(M, C5, device=dev, dtype=torch.bfloat16)
+        db5 = torch.zeros(C5, device=dev, dtype=torch.float32)
         call("wf_pool_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u),
-             _p(mask), _p(valid), B, N, C5, _p(dz), BF16, _s())
+             _p(mask), _p(valid), B, N, C5, _p(dz), BF16, _p(db5), _s())
         _count()
         if g_pf is not None and g_pf.numel() > 0:
             dz = (dz.float() + g_pf.reshape(M, C5)).to(torch.bfloat16)      # only when a caller used point_features
+            db5 = db5 + g_pf.reshape(M, C5).sum(0)
         grads = {}
         sms = _sm_count()
 
@@ -407,7 +409,7 @@ class EncoderPointMLP_TC(torch.autograd.Function):
 
         # layer 5 (no LayerNorm)
         grads["W5"] = weight_grad(dz, hs[3], C5, W5.shape[1])
-        grads["b5"] = colsum(dz)
+        grads["b5"] = db5
         dh = torch.empty(M, W5.shape[1], device=dev, dtype=torch.bfloat16)
         gemm_bf16(dz, cast_bf16(W5, transpose=True), M=M, N=W5.shape[1], K=C5, out=dh)
         for li, (W, g, be) in zip((2, 1, 0), ((W4, g4, be4), (W3, g3, be3), (W2, g2, be2))):
