@@ -230,6 +230,8 @@ def main_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms = {False: [], True: []}
+
     def timed(n, e2e):
         total_ms = 0.0
         for _ in range(n):
@@ -246,6 +248,7 @@ def main_gpu(args):
             e1.record()
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)
+            step_ms[e2e].append(round(e0.elapsed_time(e1), 3))
         return total_ms
 
     for _ in range(max(args.warmup, 3)):
@@ -305,6 +308,7 @@ def main_gpu(args):
                                     "sample": f"oracle port, 2 clouds x {POINTS} pts per step, 3 steps after 1 warm-up "
                                               f"({cms:.0f} ms/step), torch CPU {cores} threads"}
         print(json.dumps(line), flush=True)
+        print("per-step ms (device-resident):", step_ms[False], "\nper-step ms (e2e):", step_ms[True], file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 

@@ -141,8 +141,9 @@ int wf_enc_l1_bwd(const float* x, const float* W, const float* b, const float* g
  * a_kmajor/b_kmajor = 1: operand stored [rows, K] with K contiguous (activations, weights);
  * = 0: operand stored [K, rows] with rows contiguous (the dW = dZ^T * H reduction over points).
  * out_dtype WF_BF16 (store) or WF_F32 (store, or atomic accumulate when accumulate != 0, used with
- * split_k > 1).  rowstats (optional, M*2 floats, ACCUMULATED): per-row sum and sum of squares of
- * the fp32 result incl. bias -- the LayerNorm statistics of models/PointNetEncoder.py:38.
+ * split_k > 1).  rowstats (optional, wf_gemm_rowstats_parts(N) * M * 2 floats, WRITTEN): per N tile and
+ * row, the sum and sum of squares of the fp32 result incl. bias -- the LayerNorm statistics of
+ * models/PointNetEncoder.py:38, added in tile order by wf_stats_finalize (deterministic).
  * Constraints: lda/ldb % 8 == 0 (16-byte TMA strides), pointers 16-byte aligned. */
 int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M,
                  int N, int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate,
@@ -164,9 +165,10 @@ int wf_ln_relu_bf16_bwd(const void* dh, const void* z, const float* mean, const 
                         const float* gamma, const float* beta, void* dz, float* dgamma, float* dbeta,
                         float* dcolsum, int M, int C, wf_stream_t stream);
 
-/* (sum, sumsq) -> (mean, rstd) per row */
-int wf_stats_finalize(const float* rowstats, int M, int C, float eps, float* mean, float* rstd,
-                      wf_stream_t stream);
+/* rowstats[parts][M] (sum, sumsq) -> (mean, rstd) per row over C columns */
+int wf_gemm_rowstats_parts(int N);
+int wf_stats_finalize(const float* rowstats, int M, int C, int parts, float eps, float* mean,
+                      float* rstd, wf_stream_t stream);
 
 /* fp32 -> bf16 cast, optionally transposed ([R,C] -> [C,R]) -- weight staging for the GEMMs */
 int wf_cast_bf16(const float* src, int R, int C, void* dst, int transpose, wf_stream_t stream);
@@ -183,6 +185,46 @@ int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u
                 const float* g_mean_u, const int32_t* arg_m, const int32_t* arg_u,
                 const uint8_t* mask, const float* valid, int B, int N, int C, void* d_pf,
                 int d_dtype, float* dbias, wf_stream_t stream);
+
+/* Pooled reductions WITHOUT the (B,N,C) point-feature tensor (production path; north_star "the NxC activation
+ * tensor never reaches HBM").
+ * wf_gemm_bf16_pool: the final Linear of the per-point MLP (models/PointNetEncoder.py:94) as wf_gemm_bf16 (K-major
+ *   bf16 operands) whose epilogue does not store D: for every (cloud, channel) it atomically maximises a packed
+ *   64-bit word (order-preserving float bits << 32 | ~row-in-cloud) over all rows (max_u) and over rows with
+ *   mask != 0 (max_m) -> max and FIRST argmax, bit-identical to a max over the stored tensor
+ *   (models/PointNetEncoder.py:108-110, models/VertexPredictor.py:87).  Both outputs are [clouds, N] words the caller
+ *   zeroes; a cloud = points_per_cloud (>= 32) consecutive rows, row_offset = global index of row 0 (chunked calls).
+ * wf_ln_relu_bf16_fwd_colsum: wf_ln_relu_bf16_fwd that also writes per-row-block column sums of h (all rows / valid
+ *   rows) to `part` (wf_seg_part_floats(total_rows, C) floats); wf_seg_mean adds them in block order into
+ *   hbar[2][B][C] = mean over all rows, mean over valid rows (sum / valid[b]).  The mean pools of the point features
+ *   are then Linear(hbar) (models/PointNetEncoder.py:103-105, models/VertexPredictor.py:86: an affine map commutes
+ *   with the mean).  points_per_cloud >= 128, row_offset % 128 == 0.
+ * wf_pool_finalize: decodes the packed maxima, adds the bias: lin[2][B][C] = hbar W^T (no bias). */
+int wf_gemm_bf16_pool(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                      const float* bias, int points_per_cloud, int row_offset, const uint8_t* mask,
+                      uint64_t* max_u, uint64_t* max_m, wf_stream_t stream);
+int wf_ln_relu_bf16_fwd_colsum(const void* z, const float* mean, const float* rstd,
+                               const float* gamma, const float* beta, void* h, const uint8_t* mask,
+                               int M, int C, int points_per_cloud, int row_offset, float* part,
+                               wf_stream_t stream);
+int wf_seg_part_floats(int total_rows, int C);
+int wf_seg_mean(const float* part, const float* valid, int B, int points_per_cloud, int C,
+                float* hbar, wf_stream_t stream);
+int wf_pool_finalize(const uint64_t* packed_u, const uint64_t* packed_m, const float* lin,
+                     const float* bias, int B, int C, float* max_m, int32_t* arg_m, float* avg_m,
+                     float* max_u, int32_t* arg_u, float* mean_u, wf_stream_t stream);
+/* Backward of the four pools THROUGH the final Linear (W [C,K] fp32, h [B*N,K] bf16 its input) without dense GEMMs:
+ * the pooled gradients are per-cloud constants plus <= 2C single entries at the argmax rows (train.py:140 autograd
+ * reaches the same numbers through a dense (B*N,C) gradient).  dbar[2][B][K] = [g_mean_u; g_avg_m] W (caller).
+ *   dh[B*N,K] bf16 (written) = dbar_u/N + mask*dbar_m/valid + sum_{c: argmax(b,c)=n} g(b,c) W[c,:]
+ *   dW[C,K] += sum_b g(b,c) h[b,argmax(b,c),:] (caller pre-fills it with G^T hbar);  db[C] written.
+ * work: wf_pool_fused_bwd_work_ints(B, C) int32 of scratch.  Deterministic (no floating-point atomics). */
+int wf_pool_fused_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u,
+                      const float* g_mean_u, const int32_t* arg_m, const int32_t* arg_u,
+                      const uint8_t* mask, const float* valid, const float* dbar, const float* W,
+                      const void* h, int B, int N, int C, int K, int32_t* work, void* dh, float* dW,
+                      float* db, wf_stream_t stream);
+int wf_pool_fused_bwd_work_ints(int B, int C);
 
 /* ------------------------------------------------------------------------------------------
  * Edge head: ragged batch, vertices of all samples concatenated,

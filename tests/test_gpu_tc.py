@@ -28,12 +28,22 @@ def test_gemm_bf16_kmajor_fp32_out(ops, M, N, K):
     B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda")
     out = torch.full((M, N), float("nan"), device="cuda")
-    stats = torch.zeros(M, 2, device="cuda")
+    from wf_b200._lib import call
+    parts = call("wf_gemm_rowstats_parts", N)
+    stats = torch.full((parts, M, 2), float("nan"), device="cuda")
     ops.gemm_bf16(A, B, M=M, N=N, K=K, bias=bias, out=out, rowstats=stats)
     ref = A.float().double() @ B.float().double().t() + bias.double()
     assert_close(out, ref, 1e-4, f"kmajor f32 {M}x{N}x{K}")
-    assert_close(stats[:, 0], ref.sum(1), 1e-4, "rowstats sum")
-    assert_close(stats[:, 1], (ref * ref).sum(1), 1e-4, "rowstats sumsq")
+    assert_close(stats[:, :, 0].sum(0), ref.sum(1), 1e-4, "rowstats sum")
+    assert_close(stats[:, :, 1].sum(0), (ref * ref).sum(1), 1e-4, "rowstats sumsq")
+    mean = torch.empty(M, device="cuda"); rstd = torch.empty(M, device="cuda")
+    call("wf_stats_finalize", ops._p(stats), M, N, parts, 1e-5, ops._p(mean), ops._p(rstd), ops._s())
+    assert_close(mean, ref.mean(1), 1e-4, "row mean")
+    assert_close(rstd, (ref.var(1, unbiased=False) + 1e-5).rsqrt(), 1e-3, "row rstd")
+    # deterministic: a second run gives the same bits (no floating-point atomics in the forward path)
+    out2 = torch.empty_like(out); stats2 = torch.empty_like(stats)
+    ops.gemm_bf16(A, B, M=M, N=N, K=K, bias=bias, out=out2, rowstats=stats2)
+    assert torch.equal(out, out2) and torch.equal(stats, stats2)
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 512, 256), (1000, 1024, 512), (130, 264, 72)])
@@ -212,3 +222,167 @@ def test_heads_tf32_dispatch(ops):
     assert_close(a, x.double() @ W.double().t(), 1e-5, "simt")
     assert_close(b, a, 2e-3, "tf32 vs simt")
     assert not torch.equal(a, b)              # i.e. the tensor-core path really ran
+
+
+# ----------------------------------------------------------------------------------------------
+# fused pooling: max pools in the GEMM epilogue, mean pools through the affine map, analytic backward
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,K,C", [(3, 300, 256, 512), (2, 128, 64, 96), (5, 1000, 1024, 512), (1, 4099, 128, 200)])
+def test_gemm_bf16_pool_epilogue_bit_exact(ops, B, N, K, C):
+    """wf_gemm_bf16_pool: max and FIRST argmax per (cloud, channel), all rows and valid rows, must be bit-identical to
+    reducing the stored fp32 output of wf_gemm_bf16 on the same operands (tile rows straddle cloud boundaries here:
+    N is not a multiple of 128/32).  Also in row chunks (row_offset) as the inference path calls it."""
+    torch.manual_seed(B * 1000 + N)
+    M = B * N
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(C, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    # force ties: duplicate rows (same value in every channel) so that "first index" is exercised
+    A[N // 2] = A[3]; A[N - 1] = A[3]
+    bias = torch.randn(C, device="cuda")
+    mask = (torch.rand(B, N, device="cuda") > 0.3)
+    mask[:, 3] = False
+    if B > 1:
+        mask[1] = False                                   # a cloud without valid points
+    mask_u8 = mask.to(torch.uint8).contiguous()
+    pf = torch.empty(M, C, device="cuda")
+    ops.gemm_bf16(A, W, M=M, N=C, K=K, bias=bias, out=pf)
+    pf3 = pf.view(B, N, C)
+    ref_u, ref_au = pf3.max(dim=1)
+    pm = pf3.masked_fill(~mask.unsqueeze(-1), float("-inf"))
+    ref_m, ref_am = pm.max(dim=1)
+    # torch.max returns *an* index of the maximum; compute the first one explicitly
+    ar = torch.arange(N, device="cuda").view(1, N, 1)
+    first = lambda t, mx: torch.where(t == mx.unsqueeze(1), ar, N).min(dim=1).values
+    ref_au, ref_am = first(pf3, ref_u), first(pm, ref_m)
+    for chunks in (1, 3):
+        packed = torch.zeros(2, B, C, device="cuda", dtype=torch.int64)
+        step = ((M + chunks - 1) // chunks + 127) // 128 * 128
+        for r0 in range(0, M, step):
+            r1 = min(M, r0 + step)
+            ops.gemm_bf16_pool(A[r0:r1], W, M=r1 - r0, N=C, K=K, bias=bias, points_per_cloud=N, row_offset=r0,
+                               mask=mask_u8.view(-1)[r0:r1], packed=packed)
+        outs = [torch.empty(B, C, device="cuda") for _ in range(4)]
+        args = [torch.empty(B, C, device="cuda", dtype=torch.int32) for _ in range(2)]
+        lin = torch.zeros(2 * B, C, device="cuda")
+        from wf_b200._lib import call
+        call("wf_pool_finalize", ops._p(packed[0]), ops._p(packed[1]), ops._p(lin), None, B, C, ops._p(outs[0]), ops._p(args[0]),
+             ops._p(outs[1]), ops._p(outs[2]), ops._p(args[1]), ops._p(outs[3]), ops._s())
+        assert torch.equal(outs[2], ref_u), "unmasked max not bit-identical"
+        assert torch.equal(args[1].long(), ref_au), "unmasked argmax differs"
+        has = mask.any(dim=1)
+        exp_m = torch.where(has.unsqueeze(1), ref_m, torch.zeros_like(ref_m))
+        exp_am = torch.where(has.unsqueeze(1), ref_am, torch.full_like(ref_am, -1))
+        assert torch.equal(outs[0], exp_m), "masked max not bit-identical"
+        assert torch.equal(args[0].long(), exp_am), "masked argmax differs"
+
+
+def test_ln_colsum_and_seg_mean(ops):
+    """wf_ln_relu_bf16_fwd_colsum writes the same h as wf_ln_relu_bf16_fwd and wf_seg_mean returns the per-cloud means of
+    that h (all rows / valid rows) -- also when called in row chunks."""
+    from wf_b200._lib import call
+    torch.manual_seed(11)
+    B, N, C = 3, 333, 1024
+    M = B * N
+    z = (torch.randn(M, C, device="cuda") * 1.5).to(torch.bfloat16)
+    mean = z.float().mean(1).contiguous(); rstd = (z.float().var(1, unbiased=False) + 1e-5).rsqrt().contiguous()
+    g = 1 + 0.1 * torch.randn(C, device="cuda"); be = 0.1 * torch.randn(C, device="cuda")
+    mask = (torch.rand(M, device="cuda") > 0.25).to(torch.uint8)
+    valid = mask.view(B, N).sum(1).clamp_min(1).float()
+    h_ref = torch.empty_like(z)
+    call("wf_ln_relu_bf16_fwd", ops._p(z), ops._p(mean), ops._p(rstd), ops._p(g), ops._p(be), ops._p(h_ref), M, C, ops._s())
+    for step in (M, 384):
+        h = torch.zeros_like(z)
+        part = torch.empty(call("wf_seg_part_floats", M, C), device="cuda")
+        for r0 in range(0, M, step):
+            n = min(step, M - r0)
+            call("wf_ln_relu_bf16_fwd_colsum", ops._p(z[r0:]), ops._p(mean[r0:]), ops._p(rstd[r0:]), ops._p(g), ops._p(be),
+                 ops._p(h[r0:]), ops._p(mask[r0:]), n, C, N, r0, ops._p(part), ops._s())
+        assert torch.equal(h, h_ref)
+        hbar = torch.empty(2 * B, C, device="cuda")
+        call("wf_seg_mean", ops._p(part), ops._p(valid), B, N, C, ops._p(hbar), ops._s())
+        h3 = h_ref.float().view(B, N, C)
+        assert_close(hbar[:B], h3.mean(1), 1e-5, "mean of h")
+        assert_close(hbar[B:], (h3 * mask.view(B, N, 1)).sum(1) / valid.view(B, 1), 1e-5, "masked mean of h")
+
+
+def test_encoder_fused_pool_vs_unfused(ops):
+    """The whole bf16 encoder with the fused pooling against the same tensor-core path that materialises the fp32 point
+    features (WF_B200_FUSED_POOL=0 behaviour): max pools and argmax bit-identical, mean pools to fp32 rounding, and
+    all 18 parameter gradients close (the analytic backward keeps the pooled gradient in fp32 where the dense path rounds
+    it to bf16, so agreement is at bf16 level, not bitwise)."""
+    from oracle import wireframe_oracle as wo
+    from models.PointNetEncoder import PointNetEncoder
+    torch.manual_seed(0)
+    enc = PointNetEncoder().cuda()
+    sd = {k[len("encoder."):]: v for k, v in wo.make_state_dict(5, 16).items() if k.startswith("encoder.")}
+    enc.load_state_dict(sd)
+    x, _, _ = wo.make_inputs(7, 3, 900, 16, pad_frac=0.15, norm_intensity=True)
+    x = x.cuda()
+    gs = [torch.randn(3, 512, device="cuda") for _ in range(4)]
+    ops.set_precision("bf16")
+    res = {}
+    for fused in (False, True):
+        ops.FUSED_POOL = fused
+        enc.zero_grad()
+        r = enc.pooled(x)
+        (r[0] * gs[0] + r[1] * gs[1] + r[2] * gs[2] + r[3] * gs[3]).sum().backward()
+        res[fused] = ([t.detach().clone() for t in r[:6]], {k: p.grad.detach().clone() for k, p in enc.named_parameters()
+                                                            if p.grad is not None})
+    ops.FUSED_POOL = True
+    a, b = res[True][0], res[False][0]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[4], b[4]), "masked max / argmax"
+    assert torch.equal(a[2], b[2]) and torch.equal(a[5], b[5]), "unmasked max / argmax"
+    assert_close(a[1], b[1], 2e-3, "masked mean pool")
+    assert_close(a[3], b[3], 2e-3, "unmasked mean pool")
+    for k, g in res[False][1].items():
+        if k.startswith("mlp."):
+            e = _fro(res[True][1][k], g)
+            print(f"   fused vs unfused {k:16s} err {e:.3e}")
+            assert e < 3e-2, f"grad {k}: {e:.3e}"
+
+
+def test_pool_fused_bwd_matches_dense(ops):
+    """wf_pool_fused_bwd (analytic) against the dense definition in fp64: dh = d_pf W, dW = d_pf^T h, db = colsum(d_pf)
+    with d_pf built from the four pooled gradients exactly as autograd would (reference train.py:140)."""
+    from wf_b200._lib import call
+    torch.manual_seed(3)
+    B, N, C, K = 3, 257, 512, 1024
+    M = B * N
+    h = torch.relu(torch.randn(M, K, device="cuda")).to(torch.bfloat16)
+    W = torch.randn(C, K, device="cuda") / math.sqrt(K)
+    mask = (torch.rand(B, N, device="cuda") > 0.2)
+    mask[2] = False
+    valid = mask.sum(1).clamp_min(1).float()
+    arg_m = torch.randint(0, N, (B, C), device="cuda", dtype=torch.int32)
+    arg_m[:, :40] = 7                                      # many channels share one row
+    arg_m[2] = -1
+    arg_u = torch.randint(0, N, (B, C), device="cuda", dtype=torch.int32)
+    arg_u[:, :20] = 7
+    g = [torch.randn(B, C, device="cuda") for _ in range(4)]       # g_max_m, g_avg_m, g_max_u, g_mean_u
+    # dense reference
+    d_pf = torch.zeros(B, N, C, device="cuda", dtype=torch.float64)
+    d_pf += (g[3].double() / N).unsqueeze(1)
+    d_pf += mask.unsqueeze(-1).double() * (g[1].double() / valid.double().unsqueeze(1)).unsqueeze(1)
+    bi = torch.arange(B, device="cuda").unsqueeze(1).expand(B, C); ci = torch.arange(C, device="cuda").unsqueeze(0).expand(B, C)
+    okm = arg_m >= 0
+    d_pf.index_put_((bi[okm], arg_m[okm].long(), ci[okm]), g[0].double()[okm], accumulate=True)
+    d_pf.index_put_((bi, arg_u.long(), ci), g[2].double(), accumulate=True)
+    d2 = d_pf.view(M, C)
+    dh_ref = d2 @ W.double(); dW_ref = d2.t() @ h.double(); db_ref = d2.sum(0)
+    # library
+    hbar = torch.empty(2 * B, K, device="cuda")
+    h3 = h.float().view(B, N, K)
+    hbar[:B] = h3.mean(1); hbar[B:] = (h3 * mask.unsqueeze(-1)).sum(1) / valid.unsqueeze(1)
+    G = torch.cat([g[3], g[1]], 0).contiguous()
+    dbar = ops.gemm_f32(G, W, tc=False)
+    dW = ops.gemm_f32(G, hbar, transA=True, tc=False)
+    db = torch.empty(C, device="cuda")
+    work = torch.empty(call("wf_pool_fused_bwd_work_ints", B, C), device="cuda", dtype=torch.int32)
+    dh = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    mask_u8 = mask.to(torch.uint8).contiguous()
+    call("wf_pool_fused_bwd", ops._p(g[0]), ops._p(g[1]), ops._p(g[2]), ops._p(g[3]), ops._p(arg_m), ops._p(arg_u), ops._p(mask_u8),
+         ops._p(valid), ops._p(dbar), ops._p(W), ops._p(h), B, N, C, K, ops._p(work), ops._p(dh), ops._p(dW), ops._p(db), ops._s())
+    assert_close(dh.float(), dh_ref, 5e-3, "dh (bf16 storage)")
+    assert_close(dW, dW_ref, 2e-5, "dW")
+    # masked-avg term of db: the library's rule is "cloud has a valid point" (arg_m >= 0), the dense one sums the mask
+    assert_close(db, db_ref, 2e-5, "db")

@@ -202,12 +202,14 @@ l1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const fl
     }
 }
 
-__global__ void stats_finalize_kernel(const float* __restrict__ st, int M, float invC, float eps, float* __restrict__ mean,
-                                      float* __restrict__ rstd) {
+__global__ void stats_finalize_kernel(const float2* __restrict__ st, int M, int parts, float invC, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
-    const float mu = st[2 * (size_t)i] * invC;
-    const float var = fmaxf(st[2 * (size_t)i + 1] * invC - mu * mu, 0.f);
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = 0; p < parts; ++p) { const float2 t = st[(size_t)p * M + i]; s1 += t.x; s2 += t.y; }     // fixed order
+    const float mu = s1 * invC;
+    const float var = fmaxf(s2 * invC - mu * mu, 0.f);
     mean[i] = mu; rstd[i] = rsqrtf(var + eps);
 }
 
@@ -385,10 +387,13 @@ extern "C" int wf_enc_l1_bwd(const float* x, const float* W, const float* b, con
     return WF_OK;
 }
 
-extern "C" int wf_stats_finalize(const float* rowstats, int M, int C, float eps, float* mean, float* rstd, wf_stream_t stream) {
+extern "C" int wf_stats_finalize(const float* rowstats, int M, int C, int parts, float eps, float* mean, float* rstd,
+                                 wf_stream_t stream) {
     using namespace wf;
     if (M <= 0) return WF_OK;
-    enc::stats_finalize_kernel<<<cdiv(M, 256), 256, 0, as_stream(stream)>>>(rowstats, M, 1.0f / (float)C, eps, mean, rstd);
+    WF_CHECK_ARG(parts >= 1 && (reinterpret_cast<uintptr_t>(rowstats) & 7) == 0, "wf_stats_finalize: parts >= 1, 8-byte aligned rowstats");
+    enc::stats_finalize_kernel<<<cdiv(M, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(rowstats), M, parts,
+                                                                            1.0f / (float)C, eps, mean, rstd);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

@@ -48,7 +48,25 @@ struct Params {
     void* D;
     int ldd, out_dtype, accumulate;
     float* rowstats;
+    // pool mode (final encoder Linear, models/PointNetEncoder.py:94,103-111 + models/VertexPredictor.py:87): instead of
+    // storing D, every column's maximum over the rows of each cloud (pool_n consecutive rows) goes to a packed
+    // 64-bit atomicMax -- (order-preserving bits of the value << 32) | ~(row within the cloud) -- so ties resolve to the
+    // first row, exactly like torch.max(dim=1).  pool_max_u: all rows; pool_max_m: rows with mask != 0.
+    int pool_n, pool_row0;              // points per cloud (0 = off); global row index of this launch's row 0
+    const uint8_t* pool_mask;
+    unsigned long long* pool_max_u;
+    unsigned long long* pool_max_m;
 };
+
+// float -> uint32 whose unsigned order is the float order (-inf < ... < -0 < +0 < ... < +inf)
+__device__ __forceinline__ uint32_t ordered_bits(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ void pool_push(unsigned long long* addr, float v, uint32_t n) {
+    const unsigned long long pk = (static_cast<unsigned long long>(ordered_bits(v)) << 32) | (0xFFFFFFFFu - n);
+    atomicMax(addr, pk);                              // result unused -> RED.MAX.64: fire-and-forget, no round trip to L2
+}
 
 // ESZ = operand element size: 2 -> bf16 (kind::f16), 4 -> tf32 on fp32 storage (kind::tf32).
 // A_KM / B_KM: operand stored K-major ([rows, K]) or MN-major ([K, rows]).
@@ -231,6 +249,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int row0 = m_blk * BM + q * 32;
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
+            // pool mode: which of this warp's 32 rows exist / are valid points, and where the next cloud starts
+            uint32_t pool_mbits = 0; int pool_rows = 0, pool_b0 = 0, pool_rb = 32;
+            if (p.pool_n > 0) {
+                const bool mk = row_ok && (p.pool_mask == nullptr || p.pool_mask[row] != 0);
+                pool_mbits = __ballot_sync(0xffffffffu, mk);
+                pool_rows = min(32, p.M - row0);
+                pool_b0 = (p.pool_row0 + row0) / p.pool_n;
+                pool_rb = (pool_b0 + 1) * p.pool_n - (p.pool_row0 + row0);   // rows >= pool_rb belong to the next cloud
+            }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
@@ -263,7 +290,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (full || col0 + j < p.N) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
                 }
-                if (full && !p.accumulate) {
+                if (p.pool_n > 0) {
+                    // ---- stage, then lane = column: running max / first argmax over this warp's rows, per cloud
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    __syncwarp();
+                    const int col = col0 + lane;
+#pragma unroll 1
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int r_lo = seg == 0 ? 0 : pool_rb;
+                        const int r_hi = seg == 0 ? min(pool_rb, pool_rows) : pool_rows;
+                        if (r_lo >= r_hi) continue;                          // warp-uniform
+                        float mu = 0.f, mm = 0.f; int au = -1, am = -1;
+#pragma unroll 4
+                        for (int r = r_lo; r < r_hi; ++r) {
+                            const float t = stg[r * STG_LD + lane];
+                            if (au < 0 || t > mu) { mu = t; au = r; }
+                            if (((pool_mbits >> r) & 1u) && (am < 0 || t > mm)) { mm = t; am = r; }
+                        }
+                        if (col < p.N) {
+                            const int b = pool_b0 + seg;
+                            const int base = p.pool_row0 + row0 - b * p.pool_n;            // row index inside the cloud of local row 0
+                            const size_t o = (size_t)b * p.N + col;
+                            pool_push(p.pool_max_u + o, mu, (uint32_t)(base + au));
+                            if (am >= 0) pool_push(p.pool_max_m + o, mm, (uint32_t)(base + am));
+                        }
+                    }
+                    __syncwarp();
+                } else if (full && !p.accumulate) {
                     // ---- stage, then row-contiguous stores
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -317,10 +372,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
-            if (p.rowstats != nullptr && row_ok) {
-                atomicAdd(p.rowstats + 2 * (size_t)row, s1);
-                atomicAdd(p.rowstats + 2 * (size_t)row + 1, s2);
-            }
+            if (p.rowstats != nullptr && row_ok)     // one slot per (N tile, row): summed in tile order by wf_stats_finalize
+                reinterpret_cast<float2*>(p.rowstats)[(size_t)n_blk * p.M + row] = make_float2(s1, s2);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -410,10 +463,12 @@ static bool cluster_enabled() {
     return v == 1;
 }
 
+struct PoolArgs { int n, row0; const uint8_t* mask; unsigned long long* max_u; unsigned long long* max_m; };
+
 // esz 2: bf16 operands; esz 4: fp32 operands multiplied as tf32
 static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N, int K,
                    const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k, float* rowstats,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const PoolArgs* pool = nullptr) {
     const int al = 16 / esz;                                     // elements per 16 bytes
     WF_CHECK_ARG(M > 0 && N > 0 && K > 0, "wf_gemm_tc: empty problem M=%d N=%d K=%d", M, N, K);
     WF_CHECK_ARG(lda % al == 0 && ldb % al == 0, "wf_gemm_tc: lda/ldb must be multiples of %d elements (16-byte TMA strides)", al);
@@ -423,6 +478,7 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     WF_CHECK_ARG(!(accumulate && out_dtype != WF_F32), "wf_gemm_tc: accumulate needs an fp32 output");
     WF_CHECK_ARG(out_dtype == WF_F32 ? (ldd % 4 == 0) : (ldd % 8 == 0), "wf_gemm_tc: ldd alignment");
     WF_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "wf_gemm_tc: D must be 16-byte aligned");
+    WF_CHECK_ARG(pool != nullptr || D != nullptr, "wf_gemm_tc: D is null");
     if (split_k < 1) split_k = 1;
     WF_CHECK_ARG(split_k == 1 || accumulate, "wf_gemm_tc: split_k > 1 needs accumulate");
     const int BKe = 128 / esz, mnbox = 128 / esz;
@@ -462,6 +518,8 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     p.kb_per_split = cdiv(p.nkb, split_k);
     p.split_k = cdiv(p.nkb, p.kb_per_split);
     p.bias = bias; p.D = D; p.ldd = ldd; p.out_dtype = out_dtype; p.accumulate = accumulate; p.rowstats = rowstats;
+    p.pool_n = 0; p.pool_row0 = 0; p.pool_mask = nullptr; p.pool_max_u = nullptr; p.pool_max_m = nullptr;
+    if (pool != nullptr) { p.pool_n = pool->n; p.pool_row0 = pool->row0; p.pool_mask = pool->mask; p.pool_max_u = pool->max_u; p.pool_max_m = pool->max_m; }
     long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
                                 : (long long)m_units * p.tiles_n * p.split_k;
     const int workers = (int)(items < workers_max ? items : workers_max);
@@ -486,6 +544,19 @@ extern "C" int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B,
                             float* rowstats, wf_stream_t stream) {
     return wf::tc::gemm_tc(2, A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias, D, ldd, out_dtype, accumulate, split_k,
                            rowstats, wf::as_stream(stream));
+}
+
+extern "C" int wf_gemm_rowstats_parts(int N) { return wf::cdiv(N, wf::tc::BN); }
+
+extern "C" int wf_gemm_bf16_pool(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
+                                 int points_per_cloud, int row_offset, const uint8_t* mask, uint64_t* max_u,
+                                 uint64_t* max_m, wf_stream_t stream) {
+    WF_CHECK_ARG(points_per_cloud >= 32 && row_offset >= 0,
+                 "wf_gemm_bf16_pool: points_per_cloud must be >= 32 (got %d), row_offset >= 0", points_per_cloud);
+    WF_CHECK_ARG(max_u != nullptr && max_m != nullptr, "wf_gemm_bf16_pool: packed outputs required");
+    wf::tc::PoolArgs pa{points_per_cloud, row_offset, mask, reinterpret_cast<unsigned long long*>(max_u),
+                        reinterpret_cast<unsigned long long*>(max_m)};
+    return wf::tc::gemm_tc(2, A, lda, 1, B, ldb, 1, M, N, K, bias, nullptr, 8, WF_BF16, 0, 1, nullptr, wf::as_stream(stream), &pa);
 }
 
 extern "C" int wf_gemm_tf32(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, int M, int N,

@@ -42,10 +42,18 @@ SIGNATURES = {
     "wf_gemm_tf32": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, P],
     "wf_ln_relu_bf16_fwd": [P, P, P, P, P, P, I, I, P],
     "wf_ln_relu_bf16_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
-    "wf_stats_finalize": [P, I, I, F, P, P, P],
+    "wf_stats_finalize": [P, I, I, I, F, P, P, P],
+    "wf_gemm_rowstats_parts": [I],
     "wf_cast_bf16": [P, I, I, P, I, P],
     "wf_pool_fwd": [P, P, P, I, I, I, P, P, P, P, P, P, P],
     "wf_pool_bwd": [P, P, P, P, P, P, P, P, I, I, I, P, I, P, P],
+    "wf_gemm_bf16_pool": [P, I, P, I, I, I, I, P, I, I, P, P, P, P],
+    "wf_ln_relu_bf16_fwd_colsum": [P, P, P, P, P, P, P, I, I, I, I, P, P],
+    "wf_seg_part_floats": [I, I],
+    "wf_seg_mean": [P, P, I, I, I, P, P],
+    "wf_pool_finalize": [P, P, P, P, I, I, P, P, P, P, P, P, P],
+    "wf_pool_fused_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P],
+    "wf_pool_fused_bwd_work_ints": [I, I],
     "wf_gather_prefix": [P, I, I, P, I, P, P],
     "wf_scatter_prefix_add": [P, I, I, P, I, P, P],
     "wf_attn_fwd": [P, P, P, I, I, I, I, P, P, P, F, P],
@@ -59,7 +67,8 @@ SIGNATURES = {
     "wf_loss_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, F, F, P, P, P, P],
 }
 _RESTYPE = {"wf_last_error": ctypes.c_char_p}
-_NO_STATUS = {"wf_version", "wf_last_error", "wf_loss_out_floats"}
+_NO_STATUS = {"wf_version", "wf_last_error", "wf_loss_out_floats", "wf_seg_part_floats", "wf_pool_fused_bwd_work_ints",
+              "wf_gemm_rowstats_parts"}
 
 _lib = None
 

@@ -90,18 +90,18 @@ def _tc_operand_ok(t: torch.Tensor) -> bool:
             and t.data_ptr() % 16 == 0)
 
 
-def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0, bias=None):
+def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0, bias=None, tc=True):
     """C = alpha * op(A) op(B) + beta * C (+ bias), fp32 storage.
     Production precision ('bf16' mode): large, 16-byte-aligned products run on the tensor cores as TF32
     (wf_gemm_tf32, tcgen05 kind::tf32, fp32 accumulate); everything else, and the whole 'fp32' parity mode,
-    runs on the fp32 SIMT kernel (wf_gemm_f32)."""
+    runs on the fp32 SIMT kernel (wf_gemm_f32).  tc=False pins a product to the SIMT kernel."""
     A, B = _rowmajor(A), _rowmajor(B)
     M, K = (A.shape[1], A.shape[0]) if transA else A.shape
     N = B.shape[0] if transB else B.shape[1]
     kb = B.shape[1] if transB else B.shape[0]
     if kb != K:
         raise ValueError(f"gemm shape mismatch {tuple(A.shape)} {tuple(B.shape)} tA={transA} tB={transB}")
-    if (_PRECISION == "bf16" and USE_TF32_HEADS and alpha == 1.0 and beta in (0.0, 1.0) and M * N * K >= _TC_MIN_MACS
+    if (tc and _PRECISION == "bf16" and USE_TF32_HEADS and alpha == 1.0 and beta in (0.0, 1.0) and M * N * K >= _TC_MIN_MACS
             and _tc_operand_ok(A) and _tc_operand_ok(B) and (out is None or _tc_operand_ok(out))
             and (bias is None or bias.data_ptr() % 16 == 0)):
         tiles = ((M + 127) // 128) * ((N + 255) // 256)
@@ -321,6 +321,25 @@ def gemm_bf16(A, B, *, M, N, K, kmajor=True, bias=None, out, accumulate=False, s
     return out
 
 
+def gemm_bf16_pool(A, Wb, *, M, N, K, bias, points_per_cloud, row_offset, mask, packed):
+    """Final per-point Linear whose epilogue max-pools instead of storing (wf_gemm_bf16_pool).  packed: int64 [2, clouds, N]
+    (zero-initialised by the caller; [0] = all rows, [1] = valid rows)."""
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    call("wf_gemm_bf16_pool", _p(A), A.stride(0), _p(Wb), Wb.stride(0), M, N, K, _p(bias), int(points_per_cloud),
+         int(row_offset), _p(mask), _p(packed[0]), _p(packed[1]), _s())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K))
+    _count()
+
+
+FUSED_POOL = os.environ.get("WF_B200_FUSED_POOL", "1") == "1"
+_FUSED_MIN_POINTS = 128
+
+
 def cast_bf16(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     w = _f32c(w)
     R, C = w.shape
@@ -352,30 +371,56 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         W1c = _f32c(W1)
         call("wf_enc_l1_fwd", _p(x), _p(W1c), _p(b1), _p(g1), _p(be1), _p(h), BF16, M, D, W1.shape[0], 1e-5, _s())
         _count()
-        hs, zs, means, rstds, wbs = [h], [], [], [], []
-        for (W, b, g, be) in ((W2, b2, g2, be2), (W3, b3, g3, be3), (W4, b4, g4, be4)):
+        C5, K5 = W5.shape
+        fused = FUSED_POOL and not want_pf and N >= _FUSED_MIN_POINTS and 2 * C5 <= 1024
+        hs, zs, means, rstds = [h], [], [], []
+        part = None
+        layers = ((W2, b2, g2, be2), (W3, b3, g3, be3), (W4, b4, g4, be4))
+        for li, (W, b, g, be) in enumerate(layers):
             Nn, K = W.shape
             wb = cast_bf16(W)
-            wbs.append(wb)
             z = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
-            stats = torch.zeros(M, 2, device=dev, dtype=torch.float32)
+            parts = call("wf_gemm_rowstats_parts", Nn)
+            stats = torch.empty(parts, M, 2, device=dev, dtype=torch.float32)
             gemm_bf16(hs[-1], wb, M=M, N=Nn, K=K, bias=b, out=z, rowstats=stats)
             mean = torch.empty(M, device=dev, dtype=torch.float32)
             rstd = torch.empty(M, device=dev, dtype=torch.float32)
-            call("wf_stats_finalize", _p(stats), M, Nn, 1e-5, _p(mean), _p(rstd), _s())
+            call("wf_stats_finalize", _p(stats), M, Nn, parts, 1e-5, _p(mean), _p(rstd), _s())
             hn = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
-            call("wf_ln_relu_bf16_fwd", _p(z), _p(mean), _p(rstd), _p(g), _p(be), _p(hn), M, Nn, _s())
+            if fused and li == len(layers) - 1:
+                part = torch.empty(call("wf_seg_part_floats", M, Nn), device=dev, dtype=torch.float32)
+                call("wf_ln_relu_bf16_fwd_colsum", _p(z), _p(mean), _p(rstd), _p(g), _p(be), _p(hn), _p(mask), M, Nn, N, 0,
+                     _p(part), _s())
+            else:
+                call("wf_ln_relu_bf16_fwd", _p(z), _p(mean), _p(rstd), _p(g), _p(be), _p(hn), M, Nn, _s())
             _count(2)
             hs.append(hn); zs.append(z); means.append(mean); rstds.append(rstd)
         w5b = cast_bf16(W5)
-        pf = torch.empty(M, W5.shape[0], device=dev, dtype=torch.float32)
-        gemm_bf16(hs[-1], w5b, M=M, N=W5.shape[0], K=W5.shape[1], bias=b5, out=pf)
-        pooled = PoolPoints.forward(_Scratch(), pf.view(B, N, -1), mask, valid)
-        max_m, avg_m, max_u, mean_u, arg_m, arg_u = pooled
+        hbar = None
+        if fused:
+            # max pools in the GEMM epilogue, mean pools through the affine map: the (B,N,512) tensor never exists
+            packed = torch.zeros(2, B, C5, device=dev, dtype=torch.int64)
+            gemm_bf16_pool(hs[-1], w5b, M=M, N=C5, K=K5, bias=b5, points_per_cloud=N, row_offset=0, mask=mask, packed=packed)
+            hbar = torch.empty(2 * B, K5, device=dev, dtype=torch.float32)
+            call("wf_seg_mean", _p(part), _p(valid), B, N, K5, _p(hbar), _s())
+            lin = gemm_f32(hbar, _f32c(W5), transB=True, tc=False)
+            mk = lambda dt: torch.empty(B, C5, device=dev, dtype=dt)
+            max_m, avg_m, max_u, mean_u = mk(torch.float32), mk(torch.float32), mk(torch.float32), mk(torch.float32)
+            arg_m, arg_u = mk(torch.int32), mk(torch.int32)
+            call("wf_pool_finalize", _p(packed[0]), _p(packed[1]), _p(lin), _p(b5), B, C5, _p(max_m), _p(arg_m), _p(avg_m),
+                 _p(max_u), _p(arg_u), _p(mean_u), _s())
+            _count(2)
+            pf = None
+        else:
+            pf = torch.empty(M, C5, device=dev, dtype=torch.float32)
+            gemm_bf16(hs[-1], w5b, M=M, N=C5, K=K5, bias=b5, out=pf)
+            pooled = PoolPoints.forward(_Scratch(), pf.view(B, N, -1), mask, valid)
+            max_m, avg_m, max_u, mean_u, arg_m, arg_u = pooled
         ctx.save_for_backward(x, mask, valid, arg_m, arg_u, *hs, *zs, *means, *rstds, *params)
+        ctx.hbar = hbar
         ctx.dims = (B, N, D)
         ctx.mark_non_differentiable(arg_m, arg_u)
-        pf_out = pf.view(B, N, -1) if want_pf else pf.new_empty(0)
+        pf_out = pf.view(B, N, -1) if want_pf else x.new_empty(0)
         return max_m, avg_m, max_u, mean_u, arg_m, arg_u, pf_out
 
     @staticmethod
@@ -388,15 +433,7 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         M = B * N
         dev = x.device
         gs = [None if g is None else _f32c(g) for g in (g_max_m, g_avg_m, g_max_u, g_mean_u)]   # held until the launch
-        C5 = W5.shape[0]
-        dz = torch.empty(M, C5, device=dev, dtype=torch.bfloat16)
-        db5 = torch.zeros(C5, device=dev, dtype=torch.float32)
-        call("wf_pool_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u),
-             _p(mask), _p(valid), B, N, C5, _p(dz), BF16, _p(db5), _s())
-        _count()
-        if g_pf is not None and g_pf.numel() > 0:
-            dz = (dz.float() + g_pf.reshape(M, C5)).to(torch.bfloat16)      # only when a caller used point_features
-            db5 = db5 + g_pf.reshape(M, C5).sum(0)
+        C5, K5 = W5.shape
         grads = {}
         sms = _sm_count()
 
@@ -407,11 +444,38 @@ class EncoderPointMLP_TC(torch.autograd.Function):
             gemm_bf16(dzl, hin, M=Nn, N=K, K=M, kmajor=False, out=dW, accumulate=True, split_k=split)
             return dW
 
-        # layer 5 (no LayerNorm)
-        grads["W5"] = weight_grad(dz, hs[3], C5, W5.shape[1])
-        grads["b5"] = db5
-        dh = torch.empty(M, W5.shape[1], device=dev, dtype=torch.bfloat16)
-        gemm_bf16(dz, cast_bf16(W5, transpose=True), M=M, N=W5.shape[1], K=C5, out=dh)
+        hbar = ctx.hbar
+        if hbar is not None:
+            # pools -> final Linear, analytically (wf_pool_fused_bwd): no dense (M,512) gradient, no dX/dW GEMM for layer 5
+            G = torch.zeros(2 * B, C5, device=dev, dtype=torch.float32)
+            if gs[3] is not None:
+                G[:B].copy_(gs[3])
+            if gs[1] is not None:
+                G[B:].copy_(gs[1])
+            W5c = _f32c(W5)
+            dbar = gemm_f32(G, W5c, tc=False)                          # (2B, K5)
+            dW5 = gemm_f32(G, hbar, transA=True, tc=False)             # (C5, K5), argmax rows added below
+            db5 = torch.empty(C5, device=dev, dtype=torch.float32)
+            work = torch.empty(call("wf_pool_fused_bwd_work_ints", B, C5), device=dev, dtype=torch.int32)
+            dh = torch.empty(M, K5, device=dev, dtype=torch.bfloat16)
+            call("wf_pool_fused_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u), _p(mask), _p(valid),
+                 _p(dbar), _p(W5c), _p(hs[3]), B, N, C5, K5, _p(work), _p(dh), _p(dW5), _p(db5), _s())
+            _count(4)
+            grads["W5"], grads["b5"] = dW5, db5
+        else:
+            dz = torch.empty(M, C5, device=dev, dtype=torch.bfloat16)
+            db5 = torch.zeros(C5, device=dev, dtype=torch.float32)
+            call("wf_pool_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u),
+                 _p(mask), _p(valid), B, N, C5, _p(dz), BF16, _p(db5), _s())
+            _count()
+            if g_pf is not None and g_pf.numel() > 0:
+                dz = (dz.float() + g_pf.reshape(M, C5)).to(torch.bfloat16)      # only when a caller used point_features
+                db5 = db5 + g_pf.reshape(M, C5).sum(0)
+            # layer 5 (no LayerNorm)
+            grads["W5"] = weight_grad(dz, hs[3], C5, K5)
+            grads["b5"] = db5
+            dh = torch.empty(M, K5, device=dev, dtype=torch.bfloat16)
+            gemm_bf16(dz, cast_bf16(W5, transpose=True), M=M, N=K5, K=C5, out=dh)
         for li, (W, g, be) in zip((2, 1, 0), ((W4, g4, be4), (W3, g3, be3), (W2, g2, be2))):
             Nn, K = W.shape
             dzl = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
