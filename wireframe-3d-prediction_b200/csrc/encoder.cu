@@ -4,6 +4,7 @@
 #include "wf_common.cuh"
 
 #include <math_constants.h>
+#include <type_traits>
 
 namespace wf {
 namespace enc {
@@ -202,6 +203,287 @@ l1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const fl
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// layer 1, channel-stationary variant (the production kernels): a CTA of 256 threads, thread t owns channels
+// (2t, 2t+1) of all 512 for EVERY point it sees, so the weights (2 x 8), the parameter-gradient accumulators
+// (2 x 8 + 6) and LayerNorm gain/shift live in a few registers and no weight is ever re-read from shared memory.
+//
+// LayerNorm statistics without a reduction over channels: z_c = W_c.x + b_c is affine in the 8-vector x, so
+//   z_c - mean_c(z) = Wt_c.x + bt_c           (Wt = W - column mean, bt = b - mean(b): "centred" layer)
+//   var_c(z)        = x'^T S x',  x' = [x; 1],  S = (1/C) [Wt | bt]^T [Wt | bt]   (9 x 9, PSD)
+//                   = |R x'|^2  with S = R^T R (Cholesky, upper triangular R): a sum of squares, no cancellation
+// R is rebuilt per CTA in the prologue (512 x 45 products + a 9 x 9 factorisation in fp64 by one thread); each point's
+// rstd then costs 45 FMAs, done by ONE thread per point while the point is staged in shared memory.
+// Arithmetic on channel pairs uses the packed fp32 instructions (fma/mul/add.f32x2 -> FFMA2/FMUL2/FADD2).
+// ------------------------------------------------------------------------------------------
+namespace l1c {
+
+constexpr int C = 512, D = 8, NT = 256, PB = 256;       // channels, inputs, threads per CTA, points per staging block
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void up2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+struct Smem {
+    u64 xs2[PB][D];          // staged points, every coordinate duplicated into both halves (operand of the f32x2 ops)
+    u64 rs2[PB];             // (rstd, rstd) per staged point
+    float red[NT / 32][48];  // block reductions of the prologue
+    float R[48];             // packed upper-triangular factor: R[i][j], j >= i, row-major
+    float cm[12];            // column means of W (8) and mean of b
+};
+
+template <int N_>
+__device__ __forceinline__ void block_sum(Smem& s, float* v, float* out) {      // out[0..N_) valid in all threads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N_; ++i) { const float t = warp_sum(v[i]); if (lane == 0) s.red[warp][i] = t; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N_; ++i) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) t += s.red[w][i];
+        out[i] = t;
+    }
+    __syncthreads();
+}
+
+// Loads this thread's two channels, centres them, builds R.  w2[k] = (Wt[2t][k], Wt[2t+1][k]), b2 = centred bias pair.
+__device__ __forceinline__ void prologue(Smem& s, const float* __restrict__ W, const float* __restrict__ b, u64 (&w2)[D], u64& b2) {
+    const int t = threadIdx.x;
+    float w[2][D], bb[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(W + (size_t)(2 * t + i) * D), c = *reinterpret_cast<const float4*>(W + (size_t)(2 * t + i) * D + 4);
+        w[i][0] = a.x; w[i][1] = a.y; w[i][2] = a.z; w[i][3] = a.w; w[i][4] = c.x; w[i][5] = c.y; w[i][6] = c.z; w[i][7] = c.w;
+        bb[i] = b[2 * t + i];
+    }
+    float v[48], o[48];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = w[0][k] + w[1][k];
+    v[8] = bb[0] + bb[1];
+    block_sum<9>(s, v, o);
+#pragma unroll
+    for (int k = 0; k < D; ++k) { const float m = o[k] * (1.0f / C); w[0][k] -= m; w[1][k] -= m; }
+    { const float m = o[8] * (1.0f / C); bb[0] -= m; bb[1] -= m; }
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = i; j < 9; ++j) {
+            const float ai0 = i < 8 ? w[0][i] : bb[0], aj0 = j < 8 ? w[0][j] : bb[0];
+            const float ai1 = i < 8 ? w[1][i] : bb[1], aj1 = j < 8 ? w[1][j] : bb[1];
+            v[idx++] = ai0 * aj0 + ai1 * aj1;
+        }
+    block_sum<45>(s, v, o);
+    if (t == 0) {
+        // 9 x 9 Cholesky, fully unrolled so that S and R stay in registers (entries of S are sums of 512 products of O(1)
+        // numbers; fp32 with rsqrt is accurate to ~1e-6 relative on rstd, far below the bf16 output rounding)
+        float S[9][9], Rf[9][9];
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) S[i][j] = o[q++] * (1.0f / C);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            float d = S[i][i];
+#pragma unroll
+            for (int m = 0; m < i; ++m) d = fmaf(-Rf[m][i], Rf[m][i], d);
+            const bool okp = d > 1e-7f * S[i][i] && d > 0.f;                      // rank-deficient directions drop out
+            const float inv = okp ? rsqrtf(d) : 0.f;
+            Rf[i][i] = okp ? d * inv : 0.f;
+#pragma unroll
+            for (int j = i + 1; j < 9; ++j) {
+                float e = S[i][j];
+#pragma unroll
+                for (int m = 0; m < i; ++m) e = fmaf(-Rf[m][i], Rf[m][j], e);
+                Rf[i][j] = e * inv;
+            }
+        }
+        q = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) s.R[q++] = Rf[i][j];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) w2[k] = pk2(w[0][k], w[1][k]);
+    b2 = pk2(bb[0], bb[1]);
+    __syncthreads();
+}
+
+// stage up to PB points starting at p0: thread t owns point p0 + t (coordinates duplicated, rstd from the factor R)
+__device__ __forceinline__ void stage(Smem& s, const float4& xa, const float4& xb, bool ok, float eps) {
+    const int t = threadIdx.x;
+    const float xv[9] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, 1.0f};
+    float var = 0.f;
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = i; j < 9; ++j) a = fmaf(s.R[q++], xv[j], a);
+        var = fmaf(a, a, var);
+    }
+    const float rs = ok ? rsqrtf(var + eps) : 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) s.xs2[t][k] = pk2(xv[k], xv[k]);
+    s.rs2[t] = pk2(rs, rs);
+}
+
+template <int HDT>
+__global__ void __launch_bounds__(NT, 2)
+fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ g,
+           const float* __restrict__ be, void* __restrict__ h, int M, float eps) {
+    __shared__ Smem s;
+    const int t = threadIdx.x;
+    u64 w2[D], b2;
+    prologue(s, W, b, w2, b2);
+    const u64 g2 = pk2(g[2 * t], g[2 * t + 1]), be2 = pk2(be[2 * t], be[2 * t + 1]);
+    const int nblk = (M + PB - 1) / PB;
+    float4 xa = make_float4(0, 0, 0, 0), xb = xa;
+    int blk = blockIdx.x;
+    if (blk < nblk && blk * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(blk * PB + t) * D); xa = src[0]; xb = src[1]; }
+    for (; blk < nblk; blk += gridDim.x) {
+        const int p0 = blk * PB;
+        __syncthreads();                                  // previous block's readers are done with the staging buffers
+        stage(s, xa, xb, p0 + t < M, eps);
+        const int nb = blk + gridDim.x;                   // prefetch the next block's point while this one is processed
+        if (nb < nblk && nb * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(nb * PB + t) * D); xa = src[0]; xb = src[1]; }
+        __syncthreads();
+        const int np = min(PB, M - p0);
+#pragma unroll 4
+        for (int p = 0; p < np; ++p) {
+            u64 z = b2;
+#pragma unroll
+            for (int k = 0; k < D; ++k) z = fma2(s.xs2[p][k], w2[k], z);
+            const u64 y = fma2(mul2(z, s.rs2[p]), g2, be2);
+            float y0, y1;
+            up2(y, y0, y1);
+            y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f);
+            const size_t o = ((size_t)(p0 + p) * C + 2 * t) >> 1;
+            if (HDT == WF_BF16) reinterpret_cast<__nv_bfloat162*>(h)[o] = __floats2bfloat162_rn(y0, y1);
+            else reinterpret_cast<float2*>(h)[o] = make_float2(y0, y1);
+        }
+    }
+}
+
+// backward without dx.  Points are processed 8 at a time: phase 1 recomputes the layer and forms this thread's share of
+// the two LayerNorm-backward row sums, one block reduction per 8 points (warp w reduces point w), phase 2 finishes dz and
+// accumulates dW (2 x 8 per thread), db, dgamma, dbeta in registers; one atomic per entry per CTA at the end.
+constexpr int PG = 8;
+
+template <int GDT>
+__global__ void __launch_bounds__(NT, 2)
+bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ g,
+           const float* __restrict__ be, const void* __restrict__ dh, float* __restrict__ dW, float* __restrict__ db,
+           float* __restrict__ dg, float* __restrict__ dbe, int M, float eps) {
+    __shared__ Smem s;
+    __shared__ float part[PG][2][NT];                     // per point, per row sum, per thread
+    __shared__ float2 csum[PG];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    u64 w2[D], b2;
+    prologue(s, W, b, w2, b2);
+    const u64 g2 = pk2(g[2 * t], g[2 * t + 1]), be2 = pk2(be[2 * t], be[2 * t + 1]);
+    u64 aW[D], ab = 0ull, ag = 0ull, abe = 0ull;          // bit pattern 0 == (0.f, 0.f)
+#pragma unroll
+    for (int k = 0; k < D; ++k) aW[k] = 0ull;
+    const int nblk = (M + PB - 1) / PB;
+    // raw gradient words of one 8-point group: (bf16, bf16) in 32 bits, or two floats
+    typedef typename std::conditional<GDT == WF_BF16, uint32_t, float2>::type Raw;
+    Raw cur[PG], nxt[PG];
+    bool have_cur = false;
+    auto load_group = [&](Raw (&dst)[PG], int pb0, int q, int npts) {
+#pragma unroll
+        for (int i = 0; i < PG; ++i) {
+            if (q + i < npts) dst[i] = reinterpret_cast<const Raw*>(dh)[((size_t)(pb0 + q + i) * C + 2 * t) >> 1];
+            else dst[i] = Raw();
+        }
+    };
+    auto decode = [](const Raw& r, float& d0, float& d1) {
+        if constexpr (GDT == WF_BF16) { d0 = __uint_as_float(r << 16); d1 = __uint_as_float(r & 0xFFFF0000u); }
+        else { d0 = r.x; d1 = r.y; }
+    };
+    float4 xa = make_float4(0, 0, 0, 0), xb = xa;
+    int blk = blockIdx.x;
+    if (blk < nblk && blk * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(blk * PB + t) * D); xa = src[0]; xb = src[1]; }
+    for (; blk < nblk; blk += gridDim.x) {
+        const int p0 = blk * PB;
+        __syncthreads();
+        stage(s, xa, xb, p0 + t < M, eps);
+        const int nb = blk + gridDim.x;
+        if (nb < nblk && nb * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(nb * PB + t) * D); xa = src[0]; xb = src[1]; }
+        __syncthreads();
+        const int np = min(PB, M - p0);
+        if (!have_cur) { load_group(cur, p0, 0, np); have_cur = true; }
+        for (int q0 = 0; q0 < np; q0 += PG) {
+            u64 xh[PG], gy[PG];
+            // the next group's gradient words are requested now and consumed one group later (also across staging blocks)
+            if (q0 + PG < np) load_group(nxt, p0, q0 + PG, np);
+            else if (blk + (int)gridDim.x < nblk) load_group(nxt, (blk + (int)gridDim.x) * PB, 0, min(PB, M - (blk + (int)gridDim.x) * PB));
+            // ---- phase 1
+#pragma unroll
+            for (int i = 0; i < PG; ++i) {
+                const int p = q0 + i;
+                float d0, d1;
+                decode(cur[i], d0, d1);
+                u64 z = b2;
+#pragma unroll
+                for (int k = 0; k < D; ++k) z = fma2(s.xs2[p][k], w2[k], z);       // p < PB always (staging buffer is PB long)
+                xh[i] = mul2(z, s.rs2[p]);
+                float y0, y1;
+                up2(fma2(xh[i], g2, be2), y0, y1);
+                gy[i] = pk2(y0 > 0.f ? d0 : 0.f, y1 > 0.f ? d1 : 0.f);
+                const u64 gh = mul2(gy[i], g2);
+                float a0, a1, c0, c1;
+                up2(gh, a0, a1);
+                up2(mul2(gh, xh[i]), c0, c1);
+                part[i][0][t] = a0 + a1;
+                part[i][1][t] = c0 + c1;
+            }
+#pragma unroll
+            for (int i = 0; i < PG; ++i) cur[i] = nxt[i];
+            __syncthreads();
+            {   // warp w reduces point q0 + w
+                float a = 0.f, c = 0.f;
+#pragma unroll
+                for (int j = 0; j < NT / 32; ++j) { a += part[warp][0][lane + 32 * j]; c += part[warp][1][lane + 32 * j]; }
+                a = warp_sum(a); c = warp_sum(c);
+                if (lane == 0) csum[warp] = make_float2(a * (1.0f / C), c * (1.0f / C));
+            }
+            __syncthreads();
+            // ---- phase 2
+#pragma unroll
+            for (int i = 0; i < PG; ++i) {
+                const int p = q0 + i;
+                if (p < np) {                                                       // block-uniform
+                    const float2 cs = csum[i];
+                    const u64 c1 = pk2(-cs.x, -cs.x), c2 = pk2(-cs.y, -cs.y);
+                    // dz = rstd * (g*gamma - c1 - xhat*c2)
+                    const u64 dz = mul2(s.rs2[p], add2(fma2(xh[i], c2, mul2(gy[i], g2)), c1));
+                    ab = add2(ab, dz);
+                    ag = fma2(gy[i], xh[i], ag);
+                    abe = add2(abe, gy[i]);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) aW[k] = fma2(dz, s.xs2[p][k], aW[k]);
+                }
+            }
+        }
+    }
+    float lo, hi;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { up2(aW[k], lo, hi); atomicAdd(dW + (size_t)(2 * t) * D + k, lo); atomicAdd(dW + (size_t)(2 * t + 1) * D + k, hi); }
+    up2(ab, lo, hi); atomicAdd(db + 2 * t, lo); atomicAdd(db + 2 * t + 1, hi);
+    up2(ag, lo, hi); atomicAdd(dg + 2 * t, lo); atomicAdd(dg + 2 * t + 1, hi);
+    up2(abe, lo, hi); atomicAdd(dbe + 2 * t, lo); atomicAdd(dbe + 2 * t + 1, hi);
+}
+
+}  // namespace l1c
+
 __global__ void stats_finalize_kernel(const float2* __restrict__ st, int M, int parts, float invC, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,9 +645,10 @@ extern "C" int wf_enc_l1_fwd(const float* x, const float* W, const float* b, con
     if (M <= 0) return WF_OK;
     WF_CHECK_ARG(D == 8 && C == 512, "wf_enc_l1_fwd: built for D=8, C=512 (got D=%d C=%d); use wf_gemm_f32 + wf_ln_act_fwd", D, C);
     WF_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "wf_enc_l1_fwd: x must be 16-byte aligned");
-    const int grid = min(cdiv(M, 8), sm_count() * 8);
-    if (h_dtype == WF_BF16) enc::l1_fwd_kernel<8, 8, WF_BF16><<<grid, 256, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
-    else if (h_dtype == WF_F32) enc::l1_fwd_kernel<8, 8, WF_F32><<<grid, 256, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
+    WF_CHECK_ARG((reinterpret_cast<uintptr_t>(W) & 15) == 0, "wf_enc_l1_fwd: W must be 16-byte aligned");
+    const int grid = min(cdiv(M, enc::l1c::PB), sm_count() * 2);
+    if (h_dtype == WF_BF16) enc::l1c::fwd_kernel<WF_BF16><<<grid, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
+    else if (h_dtype == WF_F32) enc::l1c::fwd_kernel<WF_F32><<<grid, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
     else { set_error("wf_enc_l1_fwd: bad dtype"); return WF_EINVAL; }
     WF_LAUNCH_CHECK();
     return WF_OK;
@@ -377,6 +660,15 @@ extern "C" int wf_enc_l1_bwd(const float* x, const float* W, const float* b, con
     using namespace wf;
     if (M <= 0) return WF_OK;
     WF_CHECK_ARG(D == 8 && C == 512, "wf_enc_l1_bwd: built for D=8, C=512 (got D=%d C=%d)", D, C);
+    WF_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, "wf_enc_l1_bwd: x, W must be 16-byte aligned");
+    if (dx == nullptr) {                                   // training: no input gradient -> channel-stationary kernel
+        const int g2 = min(cdiv(M, enc::l1c::PB), sm_count() * 2);
+        if (dh_dtype == WF_BF16) enc::l1c::bwd_kernel<WF_BF16><<<g2, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, dh, dW, db, dgamma, dbeta, M, eps);
+        else if (dh_dtype == WF_F32) enc::l1c::bwd_kernel<WF_F32><<<g2, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, dh, dW, db, dgamma, dbeta, M, eps);
+        else { set_error("wf_enc_l1_bwd: bad dtype"); return WF_EINVAL; }
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
     const int grid = min(cdiv(M, 4), sm_count() * 4);
 #define WF_L1B(DT, DX) enc::l1_bwd_kernel<8, 8, DT, DX><<<grid, 256, 0, as_stream(stream)>>>(x, W, b, gamma, beta, dh, dW, db, dgamma, dbeta, dx, M, eps)
     if (dh_dtype == WF_BF16) { if (dx) WF_L1B(WF_BF16, true); else WF_L1B(WF_BF16, false); }

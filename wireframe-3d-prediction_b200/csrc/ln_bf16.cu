@@ -4,104 +4,134 @@
 //   forward : h = relu((z - mean) * rstd * gamma + beta)                  2 B read + 2 B write per element
 //   backward: g = dh * [y > 0];  gh = g * gamma;  c1 = mean(gh), c2 = mean(gh * xhat)
 //             dz = rstd * (gh - c1 - xhat * c2);  dgamma += g * xhat;  dbeta += g;  dbias += dz
-//             single pass: 4 B read + 2 B write per element.  One CTA = C/8 threads, each owning 8 consecutive channels
-//             (column partial sums stay in 24 registers); rows are processed 4 at a time with one block reduction
-//             per group; a persistent grid keeps the final atomics at 3*C per CTA.
+//             single pass: 4 B read + 2 B write per element.
+//
+// Both kernels keep a thread on 8 consecutive channels (gamma/beta and the column partial sums stay in registers) and
+// do their arithmetic on channel PAIRS with the packed fp32 instructions (fma/mul/add.f32x2 -> FFMA2/FMUL2/FADD2): the
+// 3-register scalar forms issue at half rate on sm_100, and the backward pass at ~24 scalar fp32 instructions per
+// element was bound by the fma pipe, not by HBM.
+//
+// The backward streams its operands through a shared-memory ring filled with cp.async (16 bytes per thread per row):
+// every thread copies exactly the bytes it will consume, so the only wait is its own cp.async group -- no register
+// double buffering and three row groups of loads in flight per CTA.
 #include "wf_common.cuh"
+
+#include <mutex>
 
 namespace wf {
 namespace lnb {
 
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void up2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// two bf16 in one 32-bit word -> (float(lo), float(hi))
+__device__ __forceinline__ u64 bf2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+__device__ __forceinline__ uint32_t to_bf2(u64 v) {
+    float lo, hi;
+    up2(v, lo, hi);
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&t);
 }
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    return u;
-}
-__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+__device__ __forceinline__ u64 relu2(u64 v) { float lo, hi; up2(v, lo, hi); return pk2(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
+
+__device__ __forceinline__ void load_pairs(const float* p, u64 (&f)[4]) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    f[0] = pk2(a.x, a.y); f[1] = pk2(a.z, a.w); f[2] = pk2(b.x, b.y); f[3] = pk2(b.z, b.w);
 }
 
-__global__ void __launch_bounds__(256)
-ln_relu_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, uint4* __restrict__ h, long long M, int C8) {
-    const long long total = M * C8;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long row = idx / C8;
-        const int c8 = (int)(idx - row * C8);
-        float v[8], g[8], b[8];
-        unpack8(z[idx], v);
-        load8f(gamma + c8 * 8, g); load8f(beta + c8 * 8, b);
-        const float mu = mean[row], rs = rstd[row];
+// h = relu(LN(z)) for one uint4 (8 channels) of a row with statistics (mu, rs)
+__device__ __forceinline__ uint4 ln_relu8(const uint4& u, float mu, float rs, const u64 (&gm)[4], const u64 (&bt)[4]) {
+    const u64 rs2 = pk2(rs, rs), nm2 = pk2(-mu * rs, -mu * rs);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf((v[i] - mu) * rs * g[i] + b[i], 0.f);
-        h[idx] = pack8(v);
-    }
+    for (int i = 0; i < 4; ++i) o[i] = to_bf2(relu2(fma2(fma2(bf2(w[i]), rs2, nm2), gm[i], bt[i])));
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// Same pass for the LAST LayerNorm of the per-point MLP, which also produces per-cloud column sums of its output h
-// (all rows, and rows with mask != 0).  The final Linear is affine, so the two mean pools of its output
-// (models/PointNetEncoder.py:103-105, models/VertexPredictor.py:86) are that Linear applied to the mean of h: the
-// (B,N,512) point-feature tensor never has to exist for them.  Deterministic: a CTA owns CS_R consecutive rows, a thread
-// owns 8 channels, partial sums go to part[row block][segment][kind][C] (segment 1 = rows of the next cloud when the
-// block straddles a cloud boundary) and are added in block order by seg_mean_kernel.
+// ------------------------------------------------------------------------------------------
+// forward.  A CTA (256 threads) owns CS_R consecutive rows; thread = (channel group c8, row phase rsub); four rows'
+// loads are issued before the first is used.  COLSUM (the LAST LayerNorm of the per-point MLP): also per-cloud column
+// sums of the output h (all rows / rows with mask != 0).  The final Linear is affine, so the two mean pools of its
+// output (models/PointNetEncoder.py:103-105, models/VertexPredictor.py:86) are that Linear applied to the mean of h:
+// the (B,N,512) point-feature tensor never has to exist for them.  Deterministic: partial sums go to
+// part[row block][segment][kind][C] (segment 1 = rows of the next cloud when the block straddles a cloud boundary) and are
+// added in block order by seg_mean_kernel.
+// ------------------------------------------------------------------------------------------
 constexpr int CS_R = 128;
 
-template <int C8>
+template <int C8, bool COLSUM>
 __global__ void __launch_bounds__(256)
-ln_relu_fwd_colsum_kernel(const uint4* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
-                          const float* __restrict__ gamma, const float* __restrict__ beta, uint4* __restrict__ h,
-                          const uint8_t* __restrict__ mask, int M, int pool_n, int row_off, float* __restrict__ part) {
-    constexpr int C = C8 * 8, RS = 256 / C8;
-    __shared__ float red[RS][2][C];
+ln_relu_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, uint4* __restrict__ h,
+                   const uint8_t* __restrict__ mask, int M, int pool_n, int row_off, float* __restrict__ part) {
+    constexpr int C = C8 * 8, RS = 256 / C8, UN = 4;
+    __shared__ float red[COLSUM ? RS : 1][2][COLSUM ? C : 1];
     const int tid = threadIdx.x, c8 = tid % C8, rsub = tid / C8;
     const int blk_row0 = blockIdx.x * CS_R;
     const int rows = min(CS_R, M - blk_row0);
     const int g0 = row_off + blk_row0;                       // global row of this block's first row
-    const int rb = (g0 / pool_n + 1) * pool_n - g0;          // local rows >= rb belong to the next cloud
+    const int rb = COLSUM ? (g0 / pool_n + 1) * pool_n - g0 : rows;   // local rows >= rb belong to the next cloud
     const size_t gblk = (size_t)(g0 / CS_R);
-    float gm[8], bt[8];
-    load8f(gamma + c8 * 8, gm); load8f(beta + c8 * 8, bt);
+    u64 gm[4], bt[4];
+    load_pairs(gamma + c8 * 8, gm); load_pairs(beta + c8 * 8, bt);
 #pragma unroll 1
     for (int seg = 0; seg < 2; ++seg) {
         const int r_lo = seg == 0 ? 0 : rb, r_hi = seg == 0 ? min(rb, rows) : rows;
         if (r_lo >= r_hi) break;                             // block-uniform
-        float su[8], sm[8];
+        u64 su[4], sm[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) su[i] = sm[i] = 0.f;
-        for (int r = r_lo + rsub; r < r_hi; r += RS) {
-            const size_t row = (size_t)blk_row0 + r;
-            float v[8];
-            unpack8(z[row * C8 + c8], v);
-            const float mu = mean[row], rs = rstd[row];
-            const bool mk = mask == nullptr || mask[row] != 0;
+        for (int i = 0; i < 4; ++i) su[i] = sm[i] = 0ull;
+        for (int r = r_lo + rsub; r < r_hi; r += UN * RS) {
+            uint4 u[UN];
+            float mu[UN], rs[UN];
+            bool mk[UN];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf((v[i] - mu) * rs * gm[i] + bt[i], 0.f);
-            const uint4 pk = pack8(v);
-            h[row * C8 + c8] = pk;
-            unpack8(pk, v);                                  // sum what the next GEMM will read (bf16-rounded)
+            for (int j = 0; j < UN; ++j) {
+                const int rr = r + j * RS;
+                mk[j] = false; mu[j] = 0.f; rs[j] = 0.f; u[j] = make_uint4(0, 0, 0, 0);
+                if (rr < r_hi) {
+                    const size_t row = (size_t)blk_row0 + rr;
+                    u[j] = z[row * C8 + c8]; mu[j] = mean[row]; rs[j] = rstd[row];
+                    mk[j] = COLSUM && (mask == nullptr || mask[row] != 0);
+                }
+            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { su[i] += v[i]; if (mk) sm[i] += v[i]; }
+            for (int j = 0; j < UN; ++j) {
+                const int rr = r + j * RS;
+                if (rr < r_hi) {
+                    const uint4 o = ln_relu8(u[j], mu[j], rs[j], gm, bt);
+                    h[((size_t)blk_row0 + rr) * C8 + c8] = o;
+                    if (COLSUM) {                            // sum what the next GEMM will read (bf16-rounded)
+                        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const u64 v = bf2(w[i]); su[i] = add2(su[i], v); if (mk[j]) sm[i] = add2(sm[i], v); }
+                    }
+                }
+            }
         }
+        if (COLSUM) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { red[rsub][0][c8 * 8 + i] = su[i]; red[rsub][1][c8 * 8 + i] = sm[i]; }
-        __syncthreads();
-        float* dst = part + ((gblk * 2 + seg) * 2) * C;
-        for (int i = tid; i < 2 * C; i += 256) {
-            const int kind = i / C, c = i - kind * C;
-            float t = 0.f;
+            for (int i = 0; i < 4; ++i) {
+                float lo, hi;
+                up2(su[i], lo, hi); red[rsub][0][c8 * 8 + 2 * i] = lo; red[rsub][0][c8 * 8 + 2 * i + 1] = hi;
+                up2(sm[i], lo, hi); red[rsub][1][c8 * 8 + 2 * i] = lo; red[rsub][1][c8 * 8 + 2 * i + 1] = hi;
+            }
+            __syncthreads();
+            float* dst = part + ((gblk * 2 + seg) * 2) * C;
+            for (int i = tid; i < 2 * C; i += 256) {
+                const int kind = i / C, c = i - kind * C;
+                float t = 0.f;
 #pragma unroll
-            for (int q = 0; q < RS; ++q) t += red[q][kind][c];
-            dst[(size_t)kind * C + c] = t;
+                for (int q = 0; q < RS; ++q) t += red[q][kind][c];
+                dst[(size_t)kind * C + c] = t;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -119,49 +149,84 @@ __global__ void seg_mean_kernel(const float* __restrict__ part, const float* __r
     hbar[((size_t)kind * B + b) * C + c] = t * (kind == 0 ? 1.0f / (float)pool_n : 1.0f / valid[b]);
 }
 
-constexpr int RG = 4;      // rows per group
+// ------------------------------------------------------------------------------------------
+// backward.  CTA = C/8 threads (NW warps), rows in groups of RG, STAGES groups in flight through cp.async.
+// ------------------------------------------------------------------------------------------
+constexpr int RG = 4, STAGES = 3;
 
-template <int NW>          // warps per CTA = C / 256
-__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 3 : 2)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW <= 4 ? 4 : 2)
 ln_relu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                    uint4* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum,
                    long long M) {
     constexpr int C8 = NW * 32, C = C8 * 8;
+    extern __shared__ uint4 ring[];                       // [STAGES][2 (dh, z)][RG][C8]
     __shared__ float red[2][NW][2 * RG];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float gm[8], bt[8];
-    load8f(gamma + tid * 8, gm); load8f(beta + tid * 8, bt);
-    float acc_g[8], acc_gx[8], acc_dz[8];
+    const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring)) + tid * 16;
+    u64 gm[4], bt[4];
+    load_pairs(gamma + tid * 8, gm); load_pairs(beta + tid * 8, bt);
+    u64 acc_g[4], acc_gx[4], acc_dz[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc_g[i] = acc_gx[i] = acc_dz[i] = 0.f;
+    for (int i = 0; i < 4; ++i) acc_g[i] = acc_gx[i] = acc_dz[i] = 0ull;
     const long long groups = (M + RG - 1) / RG;
-    int buf = 0;
-    for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x, buf ^= 1) {
-        const long long r0 = grp * RG;
-        uint4 ud[RG], uz[RG];
+
+    auto issue = [&](long long grp, int stage) {
+        if (grp < groups) {
+            const long long r0 = grp * RG;
 #pragma unroll
-        for (int r = 0; r < RG; ++r) {
-            if (r0 + r < M) { ud[r] = dh[(r0 + r) * C8 + tid]; uz[r] = z[(r0 + r) * C8 + tid]; }
-            else { ud[r] = make_uint4(0, 0, 0, 0); uz[r] = make_uint4(0, 0, 0, 0); }
+            for (int r = 0; r < RG; ++r) {
+                const bool ok = r0 + r < M;
+                const long long row = ok ? r0 + r : 0;                      // size 0 -> zero fill, address stays valid
+                const uint32_t d = ring_s + ((stage * 2 + 0) * RG + r) * C8 * 16;
+                cp_async16(d, dh + row * C8 + tid, ok ? 16u : 0u);
+                cp_async16(d + RG * C8 * 16, z + row * C8 + tid, ok ? 16u : 0u);
+            }
         }
-        float part[2 * RG];
-        float mu[RG], rs[RG];
+        cp_async_commit();
+    };
+
+    long long grp = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(grp + (long long)s * gridDim.x, s);
+    int stage = 0, buf = 0;
+    for (; grp < groups; grp += gridDim.x, buf ^= 1) {
+        issue(grp + (long long)(STAGES - 1) * gridDim.x, stage == 0 ? STAGES - 1 : stage - 1);
+        cp_async_wait<STAGES - 1>();                                         // this thread's copies of `grp` have landed
+        const long long r0 = grp * RG;
+        const uint4* sd = ring + ((stage * 2 + 0) * RG) * C8 + tid;
+        const uint4* sz = ring + ((stage * 2 + 1) * RG) * C8 + tid;
+        float part[2 * RG], mu[RG], rs[RG];
 #pragma unroll
         for (int r = 0; r < RG; ++r) {
             const bool ok = r0 + r < M;
             mu[r] = ok ? mean[r0 + r] : 0.f; rs[r] = ok ? rstd[r0 + r] : 0.f;
-            float d[8], x[8];
-            unpack8(ud[r], d); unpack8(uz[r], x);
-            float a = 0.f, b = 0.f;
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xh = (x[i] - mu[r]) * rs[r];
-                const float y = xh * gm[i] + bt[i];
-                const float gh = (y > 0.f ? d[i] : 0.f) * gm[i];
-                a += gh; b = fmaf(gh, xh, b);
+        for (int r = 0; r < RG; ++r) {
+            const uint4 ud = sd[r * C8], uz = sz[r * C8];
+            const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wz[4] = {uz.x, uz.y, uz.z, uz.w};
+            const u64 rs2 = pk2(rs[r], rs[r]), nm2 = pk2(-mu[r] * rs[r], -mu[r] * rs[r]);
+            u64 a = 0ull, b = 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const u64 xh = fma2(bf2(wz[i]), rs2, nm2);
+                float y0, y1, d0, d1;
+                up2(fma2(xh, gm[i], bt[i]), y0, y1);
+                up2(bf2(wd[i]), d0, d1);
+                const u64 gh = mul2(pk2(y0 > 0.f ? d0 : 0.f, y1 > 0.f ? d1 : 0.f), gm[i]);
+                a = add2(a, gh); b = fma2(gh, xh, b);
             }
-            part[2 * r] = a; part[2 * r + 1] = b;
+            float lo, hi;
+            up2(a, lo, hi); part[2 * r] = lo + hi;
+            up2(b, lo, hi); part[2 * r + 1] = lo + hi;
         }
 #pragma unroll
         for (int k = 0; k < 2 * RG; ++k) part[k] = warp_sum(part[k]);
@@ -177,26 +242,52 @@ ln_relu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, co
 #pragma unroll
             for (int w = 0; w < NW; ++w) { c1 += red[buf][w][2 * r]; c2 += red[buf][w][2 * r + 1]; }
             c1 *= (1.0f / C); c2 *= (1.0f / C);
-            float d[8], x[8], o[8];
-            unpack8(ud[r], d); unpack8(uz[r], x);
+            const uint4 ud = sd[r * C8], uz = sz[r * C8];
+            const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wz[4] = {uz.x, uz.y, uz.z, uz.w};
+            const u64 rs2 = pk2(rs[r], rs[r]), nm2 = pk2(-mu[r] * rs[r], -mu[r] * rs[r]);
+            const u64 k1 = pk2(-c1 * rs[r], -c1 * rs[r]), k2 = pk2(-c2 * rs[r], -c2 * rs[r]);
+            uint32_t o[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xh = (x[i] - mu[r]) * rs[r];
-                const float y = xh * gm[i] + bt[i];
-                const float g = y > 0.f ? d[i] : 0.f;
-                const float dzv = rs[r] * (g * gm[i] - c1 - xh * c2);
-                acc_g[i] += g; acc_gx[i] = fmaf(g, xh, acc_gx[i]); acc_dz[i] += dzv;
-                o[i] = dzv;
+            for (int i = 0; i < 4; ++i) {
+                const u64 xh = fma2(bf2(wz[i]), rs2, nm2);
+                float y0, y1, d0, d1;
+                up2(fma2(xh, gm[i], bt[i]), y0, y1);
+                up2(bf2(wd[i]), d0, d1);
+                const u64 g = pk2(y0 > 0.f ? d0 : 0.f, y1 > 0.f ? d1 : 0.f);
+                // dz = rstd * (g*gamma - c1 - xhat*c2)
+                const u64 dzv = fma2(xh, k2, fma2(mul2(g, gm[i]), rs2, k1));
+                acc_g[i] = add2(acc_g[i], g); acc_gx[i] = fma2(g, xh, acc_gx[i]); acc_dz[i] = add2(acc_dz[i], dzv);
+                o[i] = to_bf2(dzv);
             }
-            dz[(r0 + r) * C8 + tid] = pack8(o);
+            dz[(r0 + r) * C8 + tid] = make_uint4(o[0], o[1], o[2], o[3]);
         }
+        stage = stage + 1 == STAGES ? 0 : stage + 1;
     }
+    cp_async_wait<0>();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        atomicAdd(dgamma + tid * 8 + i, acc_gx[i]);
-        atomicAdd(dbeta + tid * 8 + i, acc_g[i]);
-        atomicAdd(dcolsum + tid * 8 + i, acc_dz[i]);
+    for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        up2(acc_gx[i], lo, hi); atomicAdd(dgamma + tid * 8 + 2 * i, lo); atomicAdd(dgamma + tid * 8 + 2 * i + 1, hi);
+        up2(acc_g[i], lo, hi); atomicAdd(dbeta + tid * 8 + 2 * i, lo); atomicAdd(dbeta + tid * 8 + 2 * i + 1, hi);
+        up2(acc_dz[i], lo, hi); atomicAdd(dcolsum + tid * 8 + 2 * i, lo); atomicAdd(dcolsum + tid * 8 + 2 * i + 1, hi);
     }
+}
+
+template <int NW>
+static int launch_bwd(const void* dh, const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                      void* dz, float* dgamma, float* dbeta, float* dcolsum, long long M, cudaStream_t s) {
+    constexpr int SMEM = STAGES * 2 * RG * NW * 32 * 16;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(ln_relu_bwd_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); });
+    WF_CUDA(attr_err);
+    const long long groups = (M + RG - 1) / RG;
+    const int per_sm = NW <= 4 ? 4 : 2;
+    const int grid = (int)(groups < (long long)per_sm * sm_count() ? groups : (long long)per_sm * sm_count());
+    ln_relu_bwd_kernel<NW><<<grid, NW * 32, SMEM, s>>>(static_cast<const uint4*>(dh), static_cast<const uint4*>(z), mean, rstd, gamma,
+                                                      beta, static_cast<uint4*>(dz), dgamma, dbeta, dcolsum, M);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
 }
 
 }  // namespace lnb
@@ -206,13 +297,14 @@ extern "C" int wf_ln_relu_bf16_fwd(const void* z, const float* mean, const float
                                    void* h, int M, int C, wf_stream_t stream) {
     using namespace wf;
     if (M <= 0 || C <= 0) return WF_OK;
-    WF_CHECK_ARG(C % 8 == 0, "wf_ln_relu_bf16_fwd: C %% 8 != 0");
+    WF_CHECK_ARG(C == 512 || C == 1024 || C == 2048, "wf_ln_relu_bf16_fwd: C=%d not built (512/1024/2048)", C);
     WF_CHECK_ARG(((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(gamma) |
                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "wf_ln_relu_bf16_fwd: 16-byte alignment required");
-    const long long total = (long long)M * (C / 8);
-    const int grid = (int)(cdiv(total, 256) < 16LL * sm_count() ? cdiv(total, 256) : 16LL * sm_count());
-    lnb::ln_relu_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(z), mean, rstd, gamma, beta,
-                                                                static_cast<uint4*>(h), M, C / 8);
+    const int grid = cdiv(M, lnb::CS_R);
+    cudaStream_t s = as_stream(stream);
+#define WF_LNF(C8) lnb::ln_relu_fwd_kernel<C8, false><<<grid, 256, 0, s>>>(static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(h), nullptr, M, 1, 0, nullptr)
+    if (C == 512) WF_LNF(64); else if (C == 1024) WF_LNF(128); else WF_LNF(256);
+#undef WF_LNF
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -229,7 +321,7 @@ extern "C" int wf_ln_relu_bf16_fwd_colsum(const void* z, const float* mean, cons
                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "wf_ln_relu_bf16_fwd_colsum: 16-byte alignment required");
     const int grid = cdiv(M, lnb::CS_R);
     cudaStream_t s = as_stream(stream);
-#define WF_LNC(C8) lnb::ln_relu_fwd_colsum_kernel<C8><<<grid, 256, 0, s>>>(static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(h), mask, M, points_per_cloud, row_offset, part)
+#define WF_LNC(C8) lnb::ln_relu_fwd_kernel<C8, true><<<grid, 256, 0, s>>>(static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(h), mask, M, points_per_cloud, row_offset, part)
     if (C == 512) WF_LNC(64); else if (C == 1024) WF_LNC(128); else WF_LNC(256);
 #undef WF_LNC
     WF_LAUNCH_CHECK();
@@ -261,14 +353,8 @@ extern "C" int wf_ln_relu_bf16_bwd(const void* dh, const void* z, const float* m
     WF_CHECK_ARG(((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(dz) |
                    reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
                  "wf_ln_relu_bf16_bwd: 16-byte alignment required");
-    const long long groups = ((long long)M + lnb::RG - 1) / lnb::RG;
-    const int nw = C / 256;
-    const int per_sm = nw <= 4 ? 3 : 2;
-    const int grid = (int)(groups < (long long)per_sm * sm_count() ? groups : (long long)per_sm * sm_count());
     cudaStream_t s = as_stream(stream);
-#define WF_LNB(NW) lnb::ln_relu_bwd_kernel<NW><<<grid, NW * 32, 0, s>>>(static_cast<const uint4*>(dh), static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(dz), dgamma, dbeta, dcolsum, M)
-    if (nw == 2) WF_LNB(2); else if (nw == 4) WF_LNB(4); else WF_LNB(8);
-#undef WF_LNB
-    WF_LAUNCH_CHECK();
-    return WF_OK;
+    if (C == 512) return lnb::launch_bwd<2>(dh, z, mean, rstd, gamma, beta, dz, dgamma, dbeta, dcolsum, M, s);
+    if (C == 1024) return lnb::launch_bwd<4>(dh, z, mean, rstd, gamma, beta, dz, dgamma, dbeta, dcolsum, M, s);
+    return lnb::launch_bwd<8>(dh, z, mean, rstd, gamma, beta, dz, dgamma, dbeta, dcolsum, M, s);
 }
