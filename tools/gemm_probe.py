@@ -21,7 +21,7 @@ def timeit(fn, iters=5):
 
 
 def main():
-    M = int(sys.argv[1]) if len(sys.argv) > 1 else 163840
+    M = int(sys.argv[1]) if len(sys.argv) > 1 else 640000
     dev = "cuda"
     print(f"points M={M}")
     for (K, N) in ((512, 1024), (1024, 2048), (2048, 1024), (1024, 512)):
@@ -29,11 +29,13 @@ def main():
         W = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
         bias = torch.randn(N, device=dev)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        stats = torch.zeros(M, 2, device=dev)
+        from wf_b200._lib import call
+        stats = torch.empty(call("wf_gemm_rowstats_parts", N), M, 2, device=dev)
         t = timeit(lambda: ops.gemm_bf16(A, W, M=M, N=N, K=K, bias=bias, out=out, rowstats=stats))
         tt = timeit(lambda: torch.matmul(A, W.t()))
         fl = 2.0 * M * N * K
         err = (out.float() - (A.float() @ W.float().t() + bias)).abs().max().item() if M <= 200000 else float("nan")
+        del stats
         print(f"fwd  K={K:5d} N={N:5d}: wf {t:8.3f} ms {fl / t / 1e9:8.1f} TF/s | cublas {tt:8.3f} ms {fl / tt / 1e9:8.1f} TF/s | maxerr {err:.3e}")
         # dX shape: dZ[M,N] * W[N,K] -> [M,K]  (B operand = W^T stored [K,N])
         dZ = torch.randn(M, N, device=dev).to(torch.bfloat16)

@@ -6,7 +6,8 @@
 //   CTA tile 128 x 256, K step 64 (= one 128-byte swizzle row of bf16), 4-stage TMA ring
 //   (48 KB per stage), two 256-column TMEM accumulator stages so the epilogue of tile i
 //   overlaps the MMAs of tile i+1.  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one
-//   elected lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp%4).
+//   elected lane), warp 2 = TMEM allocator, warps 4..11 = epilogue (TMEM lane quarter = warp%4, two warps per quarter
+//   splitting the tile's columns: with one warpgroup the K=512 layer was bound by the epilogue, not by the MMAs).
 //
 //   Operand layouts (both through the same 64-element-wide TMA boxes, SWIZZLE_128B):
 //     K-major  : operand stored [rows, K], K contiguous  -> descriptor LBO unused, SBO = 1024 B
@@ -34,11 +35,17 @@ constexpr int A_BYTES = BM * 128;             // 16 KB
 constexpr int B_BYTES = BN * 128;             // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BAR_BYTES = 256;
-constexpr int STG_LD = 36;                                   // floats per staged row (32 + 4 pad: conflict-free v4 access)
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;               // one 32x32 fp32 staging tile per epilogue warp
+constexpr int EPI_WARPS = 8;                                 // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int STG_TILE = 32 * 32;                            // floats: one 32x32 fp32 staging tile per epilogue warp, XOR-swizzled
+constexpr int STG_BYTES = EPI_WARPS * STG_TILE * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA)");
+
+// staging tile addressing: element (row r, column c) of a 32x32 fp32 tile; 16-byte groups are XOR-swizzled with the row so
+// that row-wise float4 writes (lane = row), row-segment float4 reads and column reads (lane = column) are all conflict-free
+__device__ __forceinline__ int stg_v4(int r, int c4) { return (r * 8 + (c4 ^ (r & 7))) * 4; }
 
 struct Params {
     int M, N, K;
@@ -109,9 +116,21 @@ struct Sched {
     }
 };
 
-template <int ESZ, bool A_KM, bool B_KM, bool MC>
+// MODE 0: one CTA per tile.  MODE 1: clusters of 2, cta_group::1 MMAs, B tile multicast (see MC above).
+// MODE 2: clusters of 2 running ONE tcgen05.mma.cta_group::2 per k-step over a 256 x 256 tile: each CTA stages its own 128
+//         rows of A and only HALF of the B tile (128 of the 256 N rows), so a k-block costs 32 KB instead of 48 KB of
+//         shared-memory fill and read per CTA -- at 128x256 per CTA the 1-SM forms are bound by shared-memory bandwidth
+//         (TMA writes + MMA operand reads ~188 B/clk of 128), the 2-SM form is not.  The leader CTA (rank 0) issues the
+//         MMAs and owns the full/tmem-empty barriers; both CTAs' TMA bytes are credited to the leader's barrier; commits
+//         are multicast so each CTA's producer and epilogue see their own barriers flip.  Six 32 KB stages.
+template <int ESZ, bool A_KM, bool B_KM, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    constexpr bool MC = MODE == 1, TWO = MODE == 2, CL = MODE != 0;
+    constexpr int NST = TWO ? 6 : STAGES;         // pipeline stages
+    constexpr int BB = TWO ? B_BYTES / 2 : B_BYTES;
+    constexpr int SB = A_BYTES + BB;              // bytes per stage (NST * SB == STAGES * STAGE_BYTES)
+    static_assert(NST * SB == STAGES * STAGE_BYTES, "ring size");
     constexpr int BK = 128 / ESZ;                 // elements of K per k-block
     constexpr int MNBOX = 128 / ESZ;              // MN-major: rows of the operand per TMA box (128 bytes)
     constexpr int BOX_BYTES = 128 * BK;           // MN-major box: BK k-rows x 128 bytes
@@ -120,34 +139,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));   // inside BAR_BYTES
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NST + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NST + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * NST + 4));   // inside BAR_BYTES
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // work items: MC -> one item per CLUSTER covers two adjacent M tiles (this CTA takes 2*pair + rank)
-    const int crank = MC ? (int)ptx::cluster_ctarank() : 0;
-    const int m_units = MC ? (p.tiles_m + 1) / 2 : p.tiles_m;
-    const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int w_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // work items: clusters -> one item per CLUSTER covers two adjacent M tiles (this CTA takes 2*pair + rank)
+    const int crank = CL ? (int)ptx::cluster_ctarank() : 0;
+    const int m_units = CL ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int w_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), MC ? 2 : 1); }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < NST; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), MC ? 2 : 1); }
+        // 2-SM: the leader's accumulator-free barrier collects the epilogue warps of both CTAs
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), TWO ? 2 * EPI_WARPS : EPI_WARPS); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (TWO) { ptx::tmem_alloc2(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS); ptx::tmem_relinquish2(); }
+        else     { ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (MC) ptx::cluster_sync();                 // peer barriers are initialised before any multicast / remote arrive
+    if (CL) ptx::cluster_sync();                 // peer barriers are initialised before any multicast / remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -158,11 +178,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             Sched sched(p, m_units, w_first, w_step);
             int n_blk, mu, kb0, kb1;
             while (sched.next(n_blk, mu, kb0, kb1)) {
-                const int m_blk = MC ? 2 * mu + crank : mu;
+                const int m_blk = CL ? 2 * mu + crank : mu;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint32_t sa = smem_base + stage * SB, sb = sa + A_BYTES;
+                    if (TWO) {
+                        // own A rows and own half of the B rows; bytes of BOTH CTAs complete on the leader's barrier
+                        const uint32_t lbar = full_bar(stage) & ptx::PEER_BIT_MASK;
+                        if (crank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * SB);
+                        if (A_KM) {
+                            ptx::tma_load_2d_2sm(sa, &map_a, lbar, kb * BK, m_blk * BM);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BM / MNBOX; ++i)
+                                ptx::tma_load_2d_2sm(sa + i * BOX_BYTES, &map_a, lbar, m_blk * BM + i * MNBOX, kb * BK);
+                        }
+                        if (B_KM) {
+                            ptx::tma_load_2d_2sm(sb, &map_b, lbar, kb * BK, n_blk * BN + crank * (BN / 2));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / MNBOX / 2; ++i)
+                                ptx::tma_load_2d_2sm(sb + i * BOX_BYTES, &map_b, lbar, n_blk * BN + crank * (BN / 2) + i * MNBOX, kb * BK);
+                        }
+                        if (++stage == NST) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), SB);
                     if (A_KM) {
                         ptx::tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m_blk * BM);
                     } else {
@@ -191,14 +232,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::idesc_f32acc(ESZ == 2 ? 1 : 2, BM, BN, A_KM ? 0 : 1, B_KM ? 0 : 1);
+        if (lane == 0 && (!TWO || crank == 0)) {
+            constexpr uint32_t idesc = ptx::idesc_f32acc(ESZ == 2 ? 1 : 2, TWO ? 2 * BM : BM, BN, A_KM ? 0 : 1, B_KM ? 0 : 1);
             // one tcgen05.mma consumes 32 bytes of K per row: K-major advances 32 B inside the swizzle row,
             // MN-major advances (32 / ESZ) k-rows of 128 B
             constexpr uint32_t LBO_A = A_KM ? 16u : (uint32_t)BOX_BYTES, LBO_B = B_KM ? 16u : (uint32_t)BOX_BYTES;
@@ -217,19 +258,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint32_t sa = smem_base + stage * SB, sb = sa + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t da = ptx::smem_desc(sa + k * KSTEP_A, LBO_A, SBO_A, LT_A);
                         const uint64_t db = ptx::smem_desc(sb + k * KSTEP_B, LBO_B, SBO_B, LT_B);
-                        if (ESZ == 2) ptx::mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        else          ptx::mma_tf32_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if (TWO) { if (ESZ == 2) ptx::mma_f16_ss2(tmem_d, da, db, idesc, accf); else ptx::mma_tf32_ss2(tmem_d, da, db, idesc, accf); }
+                        else     { if (ESZ == 2) ptx::mma_f16_ss(tmem_d, da, db, idesc, accf);  else ptx::mma_tf32_ss(tmem_d, da, db, idesc, accf); }
                     }
-                    // frees the smem stage when the MMAs retire (MC: in both CTAs -- the peer multicasts into our stage)
-                    if (MC) ptx::mma_commit_mc(empty_bar(stage), 3); else ptx::mma_commit(empty_bar(stage));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    // frees the smem stage when the MMAs retire (clusters: in both CTAs)
+                    if (TWO) ptx::mma_commit2_mc(empty_bar(stage), 3);
+                    else if (MC) ptx::mma_commit_mc(empty_bar(stage), 3);
+                    else ptx::mma_commit(empty_bar(stage));
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
-                ptx::mma_commit(tfull_bar(acc));                 // accumulator ready for the epilogue
+                if (TWO) ptx::mma_commit2_mc(tfull_bar(acc), 3);  // accumulator halves ready for both CTAs' epilogues
+                else ptx::mma_commit(tfull_bar(acc));             // accumulator ready for the epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -239,13 +284,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // shared memory so that global stores are row-contiguous (a quarter warp writes one 128-byte fp32 row segment /
         // a 64-byte bf16 segment) instead of 32 rows x 16 bytes per instruction.
         const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + q * 32 * STG_LD;
+        const int half = (warp - 4) >> 2;                        // which half of the tile's column chunks this warp owns
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (warp - 4) * STG_TILE;
         const bool bias_v4 = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
         int acc = 0; uint32_t acc_phase = 0;
         Sched sched(p, m_units, w_first, w_step);
         int n_blk, mu, kb0, kb1;
         while (sched.next(n_blk, mu, kb0, kb1)) {
-            const int m_blk = MC ? 2 * mu + crank : mu;
+            const int m_blk = CL ? 2 * mu + crank : mu;
             const int row0 = m_blk * BM + q * 32;
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
@@ -262,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ptx::tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
                 const int col0 = n_blk * BN + c * 32;
                 if (col0 >= p.N) break;                          // warp-uniform
                 uint32_t r[32];
@@ -294,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // ---- stage, then lane = column: running max / first argmax over this warp's rows, per cloud
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        *reinterpret_cast<float4*>(stg + stg_v4(lane, j >> 2)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     __syncwarp();
                     const int col = col0 + lane;
 #pragma unroll 1
@@ -305,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         float mu = 0.f, mm = 0.f; int au = -1, am = -1;
 #pragma unroll 4
                         for (int r = r_lo; r < r_hi; ++r) {
-                            const float t = stg[r * STG_LD + lane];
+                            const float t = stg[stg_v4(r, lane >> 2) + (lane & 3)];
                             if (au < 0 || t > mu) { mu = t; au = r; }
                             if (((pool_mbits >> r) & 1u) && (am < 0 || t > mm)) { mm = t; am = r; }
                         }
@@ -322,15 +368,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // ---- stage, then row-contiguous stores
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        *reinterpret_cast<float4*>(stg + stg_v4(lane, j >> 2)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     __syncwarp();
                     if (p.out_dtype == WF_BF16) {
                         const int rr = lane >> 2, cc = (lane & 3) * 8;         // 4 lanes per row, 8 columns each
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int rl = rr + 8 * i;
-                            const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cc);
-                            const float4 b = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cc + 4);
+                            const float4 a = *reinterpret_cast<const float4*>(stg + stg_v4(rl, cc >> 2));
+                            const float4 b = *reinterpret_cast<const float4*>(stg + stg_v4(rl, (cc >> 2) + 1));
                             if (row0 + rl < p.M) {
                                 uint4 pk;
                                 __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
@@ -345,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rl = rr + 4 * i;
-                            const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cc);
+                            const float4 a = *reinterpret_cast<const float4*>(stg + stg_v4(rl, cc >> 2));
                             if (row0 + rl < p.M)
                                 *reinterpret_cast<float4*>(static_cast<float*>(p.D) + (size_t)(row0 + rl) * p.ldd + col0 + cc) = a;
                         }
@@ -373,18 +419,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
             if (p.rowstats != nullptr && row_ok)     // one slot per (N tile, row): summed in tile order by wf_stats_finalize
-                reinterpret_cast<float2*>(p.rowstats)[(size_t)n_blk * p.M + row] = make_float2(s1, s2);
+                reinterpret_cast<float2*>(p.rowstats)[(size_t)(2 * n_blk + half) * p.M + row] = make_float2(s1, s2);
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (TWO) ptx::mbar_arrive_cluster(tempty_bar(acc) & ptx::PEER_BIT_MASK);     // the leader's barrier
+                else ptx::mbar_arrive(tempty_bar(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (MC) ptx::cluster_sync();                 // nobody exits while the peer may still write our smem / barriers
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CL) ptx::cluster_sync();                 // nobody exits while the peer may still write our smem / barriers
+    if (warp == 2) { if (TWO) ptx::tmem_dealloc2(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -434,7 +483,7 @@ static int make_map(CUtensorMap* m, int esz, bool mn_major, const void* ptr, uin
 
 namespace wf { namespace tc {
 
-template <int ESZ, bool A_KM, bool B_KM, bool MC>
+template <int ESZ, bool A_KM, bool B_KM, int MC>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -446,21 +495,24 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = MC ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = MC != 0 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     WF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<ESZ, A_KM, B_KM, MC>, ma, mb, p));
     return WF_OK;
 }
 
 template <int ESZ, bool A_KM, bool B_KM>
-static int launch_mc(bool mc, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
-    return mc ? launch<ESZ, A_KM, B_KM, true>(ma, mb, p, grid, s) : launch<ESZ, A_KM, B_KM, false>(ma, mb, p, grid, s);
+static int launch_mc(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
+    if (mode == 2) return launch<ESZ, A_KM, B_KM, 2>(ma, mb, p, grid, s);
+    if (mode == 1) return launch<ESZ, A_KM, B_KM, 1>(ma, mb, p, grid, s);
+    return launch<ESZ, A_KM, B_KM, 0>(ma, mb, p, grid, s);
 }
 
-static bool cluster_enabled() {
+// WF_B200_GEMM_MODE: 2 (default) = 2-SM MMA, 1 = 1-SM MMA with multicast B, 0 = no clusters
+static int cluster_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("WF_B200_GEMM_CLUSTER"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
+    if (v < 0) { const char* e = getenv("WF_B200_GEMM_MODE"); v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    return v;
 }
 
 struct PoolArgs { int n, row0; const uint8_t* mask; unsigned long long* max_u; unsigned long long* max_m; };
@@ -487,7 +539,8 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     if (a_kmajor) { if ((rc = make_map(&ma, esz, false, A, K, M, lda, BKe, BM)) != WF_OK) return rc; }
     else          { if ((rc = make_map(&ma, esz, true, A, M, K, lda, mnbox, BKe)) != WF_OK) return rc; }
     // multicast pairs pay off when there are at least two M tiles to pair up
-    const bool mc = cluster_enabled() && cdiv(M, BM) >= 2 && sm_count() >= 2;
+    const int mode = (cdiv(M, BM) >= 2 && sm_count() >= 2) ? cluster_mode() : 0;
+    const bool mc = mode != 0;
     if (b_kmajor) { if ((rc = make_map(&mb, esz, false, B, K, N, ldb, BKe, mc ? BN / 2 : BN)) != WF_OK) return rc; }
     else          { if ((rc = make_map(&mb, esz, true, B, N, K, ldb, mnbox, BKe)) != WF_OK) return rc; }
     Params p;
@@ -526,14 +579,14 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     const int grid = mc ? 2 * workers : workers;
     const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
     switch (key) {
-        case 3: return launch_mc<2, true, true>(mc, ma, mb, p, grid, stream);
-        case 2: return launch_mc<2, true, false>(mc, ma, mb, p, grid, stream);
-        case 1: return launch_mc<2, false, true>(mc, ma, mb, p, grid, stream);
-        case 0: return launch_mc<2, false, false>(mc, ma, mb, p, grid, stream);
-        case 7: return launch_mc<4, true, true>(mc, ma, mb, p, grid, stream);
-        case 6: return launch_mc<4, true, false>(mc, ma, mb, p, grid, stream);
-        case 5: return launch_mc<4, false, true>(mc, ma, mb, p, grid, stream);
-        default: return launch_mc<4, false, false>(mc, ma, mb, p, grid, stream);
+        case 3: return launch_mc<2, true, true>(mode, ma, mb, p, grid, stream);
+        case 2: return launch_mc<2, true, false>(mode, ma, mb, p, grid, stream);
+        case 1: return launch_mc<2, false, true>(mode, ma, mb, p, grid, stream);
+        case 0: return launch_mc<2, false, false>(mode, ma, mb, p, grid, stream);
+        case 7: return launch_mc<4, true, true>(mode, ma, mb, p, grid, stream);
+        case 6: return launch_mc<4, true, false>(mode, ma, mb, p, grid, stream);
+        case 5: return launch_mc<4, false, true>(mode, ma, mb, p, grid, stream);
+        default: return launch_mc<4, false, false>(mode, ma, mb, p, grid, stream);
     }
 }
 
@@ -546,7 +599,7 @@ extern "C" int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B,
                            rowstats, wf::as_stream(stream));
 }
 
-extern "C" int wf_gemm_rowstats_parts(int N) { return wf::cdiv(N, wf::tc::BN); }
+extern "C" int wf_gemm_rowstats_parts(int N) { return 2 * wf::cdiv(N, wf::tc::BN); }
 
 extern "C" int wf_gemm_bf16_pool(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                                  int points_per_cloud, int row_offset, const uint8_t* mask, uint64_t* max_u,
