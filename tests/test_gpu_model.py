@@ -211,3 +211,30 @@ def test_lazy_point_pool_proj_like_reference():
     m(x, torch.tensor([3, 4], device="cuda"))
     assert sum(p.numel() for p in m.parameters()) == n0 + 524800
     assert m.vertex_predictor.point_pool_proj.weight.is_cuda
+
+
+def test_loss_raises_scipy_errors_immediately_or_deferred():
+    """NaN predictions make scipy raise inside the reference's forward (losses/WireframeLoss.py:236).  check_status=True
+    reproduces that; the default "deferred" raises the same ValueError at the next call / check_pending() without a
+    device->host sync inside the step."""
+    from losses.WireframeLoss import WireframeLoss
+    B, V = 3, 8
+    torch.manual_seed(0)
+    good = {"vertices": torch.rand(B, V, 3, device="cuda"), "existence_probabilities": torch.rand(B, V, device="cuda"),
+            "edge_probs": torch.rand(B, 6, device="cuda")}
+    bad = {k: v.clone() for k, v in good.items()}
+    bad["vertices"][1, 2, 0] = float("nan")
+    tgt = {"vertices": torch.rand(B, V, 3, device="cuda"), "vertex_existence": torch.ones(B, V, device="cuda"),
+           "edge_labels": torch.ones(B, 6, device="cuda"), "vertex_counts": torch.tensor([4, 4, 4], device="cuda")}
+    crit = WireframeLoss()
+    crit.check_status = True
+    with pytest.raises(ValueError, match="invalid numeric"):
+        crit(bad, tgt)
+    crit.check_status = "deferred"
+    crit(bad, tgt)                                   # no exception yet
+    with pytest.raises(ValueError, match="invalid numeric"):
+        crit(good, tgt)                              # surfaces at the next call
+    crit(bad, tgt)
+    with pytest.raises(ValueError, match="invalid numeric"):
+        crit.check_pending()
+    crit(good, tgt); crit.check_pending()            # clean

@@ -20,23 +20,50 @@ class WireframeLoss(nn.Module):
         self.existence_weight = existence_weight
         self.smooth_l1_loss = nn.SmoothL1Loss()      # kept for attribute parity; the kernels implement beta=1
         self.bce_loss = nn.BCELoss()
-        self.check_status = True                     # set False to skip the per-step status read (one D2H sync)
+        # The reference gets scipy's ValueError (infeasible / invalid cost matrix, i.e. NaN or inf predictions) inside
+        # forward, because it synchronises with the device B times per call anyway.  Here the solver's status words are
+        #   True       read back immediately (one device->host sync per call; what _hungarian_matching() always does),
+        #   "deferred" copied to pinned memory asynchronously and checked at the start of the NEXT call or by
+        #              check_pending() -- same exception, one step later, no sync inside the step (default),
+        #   False      never read.
+        self.check_status = "deferred"
+        self._pending = None
 
-    def _match_device(self, predictions, targets):
+    @staticmethod
+    def _raise_for(st):
+        if any(s == LSAP_INFEASIBLE for s in st):
+            raise ValueError("cost matrix is infeasible")              # scipy's message (reference Q9)
+        if any(s == LSAP_INVALID for s in st):
+            raise ValueError("matrix contains invalid numeric entries")
+
+    def check_pending(self):
+        """Raise the ValueError of the last forward() if its assignment problems were infeasible/invalid."""
+        if self._pending is not None:
+            buf, ev = self._pending
+            self._pending = None
+            ev.synchronize()
+            self._raise_for(buf.tolist())
+
+    def _match_device(self, predictions, targets, sync=None):
+        mode = self.check_status if sync is None else sync
+        if mode == "deferred":
+            self.check_pending()
         col, status, _ = ops.loss_match(predictions['vertices'], predictions['existence_probabilities'],
                                         targets['vertices'], targets['vertex_counts'])
-        if self.check_status:
-            st = status.tolist()
-            if any(s == LSAP_INFEASIBLE for s in st):
-                raise ValueError("cost matrix is infeasible")              # scipy's message (reference Q9)
-            if any(s == LSAP_INVALID for s in st):
-                raise ValueError("matrix contains invalid numeric entries")
+        if mode is True:
+            self._raise_for(status.tolist())
+        elif mode == "deferred":
+            buf = torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
+            buf.copy_(status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending = (buf, ev)
         return col
 
     def _hungarian_matching(self, predictions, targets):
         """Reference API (losses/WireframeLoss.py:106): list of (pred_indices, target_indices) numpy int64
         arrays per sample, dummy-column assignments filtered out."""
-        col = self._match_device(predictions, targets).cpu().numpy()
+        col = self._match_device(predictions, targets, sync=True).cpu().numpy()
         counts = targets['vertex_counts'].cpu().numpy()
         out = []
         for b in range(col.shape[0]):

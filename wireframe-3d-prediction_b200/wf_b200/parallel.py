@@ -60,6 +60,12 @@ class GradAllReduce:
 
     # ---- step protocol: zero() -> forward/backward -> finish() -> optimizer.step()
     def zero(self) -> None:
+        if self.world == 1:
+            # single process: nothing to reduce -- plain zero_grad(set_to_none=True) (train.py:138), autograd then adopts
+            # the kernels' gradient tensors instead of adding them into a flat buffer
+            for p in self.module.parameters():
+                p.grad = None
+            return
         if self._built:
             self.flat.zero_()
             for b in self.buckets:
@@ -71,6 +77,8 @@ class GradAllReduce:
         self._handles = []
 
     def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if self.world == 1:
+            return
         if not self._built:
             self._order.append(p)
             return
@@ -96,6 +104,8 @@ class GradAllReduce:
     def finish(self) -> None:
         """Call after backward().  First step: builds the flat buffer/buckets from the observed gradient order and
         reduces everything at once; later steps: waits for the in-flight bucket reductions."""
+        if self.world == 1:
+            return
         if not self._built:
             self._build()
             if self.world > 1:
