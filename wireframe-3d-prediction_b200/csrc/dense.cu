@@ -210,6 +210,213 @@ ln_act_bwd_kernel(const void* __restrict__ dout, const void* __restrict__ z, con
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Vectorised fp32 LayerNorm+activation kernels (C % 4 == 0): a row is owned by NT threads -- one warp (C <= 1024: the
+// edge head's E x {128,256,512} tensors, reductions by shuffles only) or a whole CTA of 256 threads (C up to 8192: the
+// 64-row heads, where a row per CTA is what gives the launch any parallelism).  Thread t holds float4 columns
+// t + NT*i, i < VPT, of its row in registers: one pass over memory forward, one pass backward.
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ float row_sum(float v, float* red) {          // red: NT/32 floats of shared memory (NT > 32)
+    v = warp_sum(v);
+    if (NT == 32) return v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += red[w];
+    return t;
+}
+
+template <int NT, int VPT>
+__global__ void __launch_bounds__(256)
+ln_act_fwd_v4_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                     const float* __restrict__ residual, const uint8_t* __restrict__ keep, float keep_scale,
+                     float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, int M, int C, float eps) {
+    __shared__ float red[8];
+    const int t = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+    const int rows_per_cta = 256 / NT;
+    const int C4 = C >> 2;
+    float4 gm[VPT], bt[VPT];
+    if (gamma != nullptr) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int j = t + NT * i;
+            gm[i] = j < C4 ? reinterpret_cast<const float4*>(gamma)[j] : make_float4(0, 0, 0, 0);
+            bt[i] = j < C4 ? reinterpret_cast<const float4*>(beta)[j] : make_float4(0, 0, 0, 0);
+        }
+    }
+    for (int row = blockIdx.x * rows_per_cta + (NT == 32 ? (threadIdx.x >> 5) : 0); row < M; row += gridDim.x * rows_per_cta) {
+        const size_t base4 = (size_t)row * C4;
+        float4 v[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int j = t + NT * i;
+            v[i] = j < C4 ? reinterpret_cast<const float4*>(z)[base4 + j] : make_float4(0, 0, 0, 0);
+        }
+        float mu = 0.f, rs = 1.f;
+        if (gamma != nullptr) {
+            float sm = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPT; ++i) sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            mu = row_sum<NT>(sm, red) / (float)C;
+            float var = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPT; ++i) {
+                if (t + NT * i < C4) {
+                    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+                    var += a * a + b * b + c * c + d * d;
+                }
+            }
+            rs = rsqrtf(row_sum<NT>(var, red) / (float)C + eps);
+            if (t == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+        }
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int j = t + NT * i;
+            if (j >= C4) continue;
+            float y[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            if (gamma != nullptr) {
+                const float g4[4] = {gm[i].x, gm[i].y, gm[i].z, gm[i].w}, b4[4] = {bt[i].x, bt[i].y, bt[i].z, bt[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y[e] = (y[e] - mu) * rs * g4[e] + b4[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[e] = act_f(act, y[e]);
+            if (keep != nullptr) {
+                const uchar4 k = reinterpret_cast<const uchar4*>(keep)[base4 + j];
+                y[0] = k.x ? y[0] * keep_scale : 0.f; y[1] = k.y ? y[1] * keep_scale : 0.f;
+                y[2] = k.z ? y[2] * keep_scale : 0.f; y[3] = k.w ? y[3] * keep_scale : 0.f;
+            }
+            if (residual != nullptr) {
+                const float4 r = reinterpret_cast<const float4*>(residual)[base4 + j];
+                y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+            }
+            reinterpret_cast<float4*>(out)[base4 + j] = make_float4(y[0], y[1], y[2], y[3]);
+        }
+    }
+}
+
+// backward: column partial sums (dgamma, dbeta, bias gradient) stay in 12*VPT registers over all rows a thread sees;
+// NT == 32: the CTA's 8 warps are combined through shared memory first, then one atomic per column per CTA.
+template <int NT, int VPT>
+__global__ void __launch_bounds__(256)
+ln_act_bwd_v4_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd, int act,
+                     const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ dz, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dcolsum, int M, int C, int rows_per_owner) {
+    __shared__ float red[8];
+    __shared__ float comb[NT == 32 ? 8 : 1][NT == 32 ? 3 * 4 * VPT * 32 : 1];
+    const int t = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+    const int owner = NT == 32 ? blockIdx.x * 8 + (threadIdx.x >> 5) : blockIdx.x;      // a warp or a CTA
+    const int C4 = C >> 2;
+    const bool has_ln = gamma != nullptr;
+    float4 gm[VPT], bt[VPT];
+    float acc_g[VPT][4], acc_gx[VPT][4], acc_dz[VPT][4];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int j = t + NT * i;
+        gm[i] = (has_ln && j < C4) ? reinterpret_cast<const float4*>(gamma)[j] : make_float4(1, 1, 1, 1);
+        bt[i] = (has_ln && j < C4) ? reinterpret_cast<const float4*>(beta)[j] : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc_g[i][e] = acc_gx[i][e] = acc_dz[i][e] = 0.f;
+    }
+    const int r_begin = owner * rows_per_owner, r_end = min(M, r_begin + rows_per_owner);
+    for (int row = r_begin; row < r_end; ++row) {
+        const size_t base4 = (size_t)row * C4;
+        const float mu = has_ln ? mean[row] : 0.f, rs = has_ln ? rstd[row] : 1.f;
+        float xh[VPT][4], g[VPT][4];
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int j = t + NT * i;
+            if (j < C4) {
+                const float4 zv = reinterpret_cast<const float4*>(z)[base4 + j];
+                const float4 dv = reinterpret_cast<const float4*>(dout)[base4 + j];
+                const float z4[4] = {zv.x, zv.y, zv.z, zv.w};
+                float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+                if (keep != nullptr) {
+                    const uchar4 k = reinterpret_cast<const uchar4*>(keep)[base4 + j];
+                    d4[0] = k.x ? d4[0] * keep_scale : 0.f; d4[1] = k.y ? d4[1] * keep_scale : 0.f;
+                    d4[2] = k.z ? d4[2] * keep_scale : 0.f; d4[3] = k.w ? d4[3] * keep_scale : 0.f;
+                }
+                const float g4[4] = {gm[i].x, gm[i].y, gm[i].z, gm[i].w}, b4[4] = {bt[i].x, bt[i].y, bt[i].z, bt[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    xh[i][e] = has_ln ? (z4[e] - mu) * rs : z4[e];
+                    const float y = has_ln ? xh[i][e] * g4[e] + b4[e] : z4[e];
+                    g[i][e] = d4[e] * act_grad_f(act, y);
+                    const float gh = g[i][e] * g4[e];
+                    a += gh; b = fmaf(gh, xh[i][e], b);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xh[i][e] = g[i][e] = 0.f;
+            }
+        }
+        float c1 = 0.f, c2 = 0.f;
+        if (has_ln) { c1 = row_sum<NT>(a, red) / (float)C; c2 = row_sum<NT>(b, red) / (float)C; }
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int j = t + NT * i;
+            if (j >= C4) continue;
+            const float g4[4] = {gm[i].x, gm[i].y, gm[i].z, gm[i].w};
+            float d[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (has_ln) {
+                    d[e] = rs * (g[i][e] * g4[e] - c1 - xh[i][e] * c2);
+                    acc_g[i][e] += g[i][e]; acc_gx[i][e] = fmaf(g[i][e], xh[i][e], acc_gx[i][e]);
+                } else {
+                    d[e] = g[i][e];
+                }
+                acc_dz[i][e] += d[e];
+            }
+            reinterpret_cast<float4*>(dz)[base4 + j] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    }
+    if (NT == 32) {
+        // combine the 8 warps of the CTA, then one atomic per column
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int slot = (i * 4 + e) * 32 + t;
+                comb[warp][slot] = acc_gx[i][e]; comb[warp][4 * VPT * 32 + slot] = acc_g[i][e]; comb[warp][8 * VPT * 32 + slot] = acc_dz[i][e];
+            }
+        __syncthreads();
+        for (int s = threadIdx.x; s < 3 * 4 * VPT * 32; s += 256) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += comb[w][s];
+            const int kind = s / (4 * VPT * 32), r = s - kind * (4 * VPT * 32);
+            const int ie = r >> 5, tt = r & 31, i = ie >> 2, e = ie & 3;
+            const int c = 4 * (tt + 32 * i) + e;
+            if (c < C) {
+                if (kind == 0) { if (has_ln && dgamma) atomicAdd(dgamma + c, v); }
+                else if (kind == 1) { if (has_ln && dbeta) atomicAdd(dbeta + c, v); }
+                else if (dcolsum) atomicAdd(dcolsum + c, v);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int j = t + NT * i;
+            if (j >= C4) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * j + e;
+                if (has_ln && dgamma) atomicAdd(dgamma + c, acc_gx[i][e]);
+                if (has_ln && dbeta) atomicAdd(dbeta + c, acc_g[i][e]);
+                if (dcolsum) atomicAdd(dcolsum + c, acc_dz[i][e]);
+            }
+        }
+    }
+}
+
 // column sums: block (32 columns x 8 row lanes), chunk of rows per block, one atomic per column
 template <int DT>
 __global__ void colsum_kernel(const void* __restrict__ x, int M, int C, int ld, float* __restrict__ out, int rows_per_block) {
@@ -304,8 +511,26 @@ extern "C" int wf_ln_act_fwd(const void* z, int z_dtype, const float* gamma, con
     if (M <= 0 || C <= 0) return WF_OK;
     WF_CHECK_ARG(!(gamma && !beta), "wf_ln_act_fwd: gamma without beta");
     WF_CHECK_ARG(!(stats_in && (!mean || !rstd)), "wf_ln_act_fwd: stats_in needs mean/rstd");
-    dim3 grid(cdiv(M, 8));
     cudaStream_t s = as_stream(stream);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+                        reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(keep) & 3) == 0;
+    if (z_dtype == WF_F32 && out_dtype == WF_F32 && !stats_in && C % 4 == 0 && C <= 8192 && al16) {
+        const float* zf = static_cast<const float*>(z); const float* rf = static_cast<const float*>(residual);
+        float* of = static_cast<float*>(out);
+#define WF_LNV(NT, VPT, G) ln_act_fwd_v4_kernel<NT, VPT><<<G, 256, 0, s>>>(zf, gamma, beta, act, rf, keep, keep_scale, of, mean, rstd, M, C, eps)
+        if (C <= 512 || (C <= 1024 && M >= 4096)) {          // warp per row
+            const int g = min(cdiv(M, 8), sm_count() * 16);
+            if (C <= 128) WF_LNV(32, 1, g); else if (C <= 256) WF_LNV(32, 2, g); else if (C <= 512) WF_LNV(32, 4, g); else WF_LNV(32, 8, g);
+        } else {                                              // CTA per row
+            const int g = min(M, sm_count() * 16);
+            if (C <= 1024) WF_LNV(256, 1, g); else if (C <= 2048) WF_LNV(256, 2, g); else if (C <= 4096) WF_LNV(256, 4, g); else WF_LNV(256, 8, g);
+        }
+#undef WF_LNV
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
+    dim3 grid(cdiv(M, 8));
 #define WF_LNF(ZD, OD) ln_act_fwd_kernel<ZD, OD><<<grid, 256, 0, s>>>(z, gamma, beta, act, residual, keep, keep_scale, out, mean, rstd, stats_in, M, C, eps)
     if (z_dtype == WF_F32 && out_dtype == WF_F32) WF_LNF(WF_F32, WF_F32);
     else if (z_dtype == WF_BF16 && out_dtype == WF_BF16) WF_LNF(WF_BF16, WF_BF16);
@@ -345,6 +570,28 @@ extern "C" int wf_ln_act_bwd(const void* dout, int dout_dtype, const void* z, in
     WF_CHECK_ARG(!(gamma && (!beta || !mean || !rstd)), "wf_ln_act_bwd: LayerNorm backward needs beta, mean, rstd");
     cudaStream_t s = as_stream(stream);
     int rc;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dz) |
+                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(keep) & 3) == 0;
+    if (dout_dtype == WF_F32 && z_dtype == WF_F32 && dz_dtype == WF_F32 && C % 4 == 0 && C <= 8192 && al16) {
+        const float* df = static_cast<const float*>(dout); const float* zf = static_cast<const float*>(z);
+        float* of = static_cast<float*>(dz);
+#define WF_LNV(NT, VPT, G, RPO) ln_act_bwd_v4_kernel<NT, VPT><<<G, 256, 0, s>>>(df, zf, gamma, beta, mean, rstd, act, keep, keep_scale, of, dgamma, dbeta, dcolsum, M, C, RPO)
+        if (C <= 512) {                                       // warp per row; a warp owns rpo consecutive rows
+            int rpo = cdiv(M, sm_count() * 8 * 8);            // ~8 CTAs of 8 warps per SM
+            rpo = rpo < 1 ? 1 : (rpo > 16 ? 16 : rpo);
+            const int g = cdiv(M, 8 * rpo);
+            if (C <= 128) WF_LNV(32, 1, g, rpo); else if (C <= 256) WF_LNV(32, 2, g, rpo); else WF_LNV(32, 4, g, rpo);
+        } else {                                              // CTA per row(s)
+            int rpo = cdiv(M, sm_count() * 8);
+            rpo = rpo < 1 ? 1 : rpo;
+            const int g = cdiv(M, rpo);
+            if (C <= 1024) WF_LNV(256, 1, g, rpo); else if (C <= 2048) WF_LNV(256, 2, g, rpo); else if (C <= 4096) WF_LNV(256, 4, g, rpo); else WF_LNV(256, 8, g, rpo);
+        }
+#undef WF_LNV
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
     if (dout_dtype == WF_F32 && z_dtype == WF_F32 && dz_dtype == WF_F32)
         rc = launch_ln_bwd<WF_F32, WF_F32, WF_F32>(dout, z, gamma, beta, mean, rstd, act, keep, keep_scale, dz, dgamma, dbeta, dcolsum, M, C, s);
     else if (dout_dtype == WF_BF16 && z_dtype == WF_BF16 && dz_dtype == WF_BF16)

@@ -306,6 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
+            const bool add_bias = p.bias != nullptr && kb0 == 0;       // split-K: the first K range carries the bias
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
             for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
@@ -318,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const bool full = col0 + 32 <= p.N;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias != nullptr) {
+                if (add_bias) {
                     if (full && bias_v4) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -557,7 +558,7 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
         // item count fills whole waves of workers (>= 95 %), which is what removes the wave-quantisation loss.
         const long long tiles = (long long)m_units * p.tiles_n;
         int best = 1; double best_eff = 0.0;
-        const int smax = p.nkb / 8 < 64 ? (p.nkb / 8 < 1 ? 1 : p.nkb / 8) : 64;
+        const int smax = p.nkb / 4 < 64 ? (p.nkb / 4 < 1 ? 1 : p.nkb / 4) : 64;
         for (int sp = 1; sp <= smax; ++sp) {
             const long long it = tiles * sp;
             const long long waves = (it + workers_max - 1) / workers_max;

@@ -58,9 +58,12 @@ class EdgePredictor(nn.Module):
         o = ops.AttentionCore.apply(qkv, rg, ka, kas)
         f = ops.linear_ln_act(o, att.out_proj.weight, att.out_proj.bias, residual=f)       # reference :114
         W1 = em[0].weight                                                                   # (512, 1031)
-        P = ops.linear_ln_act(verts, W1[:, 2 * H:2 * H + 3], residual=ops.linear_ln_act(f, W1[:, :H]))
-        Q = ops.linear_ln_act(verts, W1[:, 2 * H + 3:2 * H + 6], residual=ops.linear_ln_act(f, W1[:, H:2 * H]))
-        z1 = ops.EdgePairLayer.apply(P, Q, verts, W1[:, 2 * H + 6], em[0].bias, rg)
+        # first edge layer on [f_i | f_j | v_i | v_j | dist] = P[i] + Q[j] + w*dist: both feature blocks in ONE product
+        # against the stacked, contiguous (1024, 512) weight (the 1031-wide rows are not 16-byte aligned for TMA)
+        Wf = torch.cat([W1[:, :H], W1[:, H:2 * H]], dim=0)
+        Wv = torch.cat([W1[:, 2 * H:2 * H + 3], W1[:, 2 * H + 3:2 * H + 6]], dim=0)
+        PQ = ops.linear_ln_act(verts, Wv, residual=ops.linear_ln_act(f, Wf))               # (T, 1024)
+        z1 = ops.EdgePairLayer.apply(PQ[:, :H], PQ[:, H:], verts, W1[:, 2 * H + 6], em[0].bias, rg)
         k, ks = self._keep((rg.E, H), em[3], dev)
         e = ops.LNAct.apply(z1, em[1].weight, em[1].bias, ACT_GELU, k, ks)
         k, ks = self._keep((rg.E, H // 2), em[7], dev)

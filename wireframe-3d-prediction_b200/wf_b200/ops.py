@@ -106,7 +106,9 @@ def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0,
             and (bias is None or bias.data_ptr() % 16 == 0)):
         tiles = ((M + 127) // 128) * ((N + 255) // 256)
         split = 1
-        if transA and bias is None and K >= 1024:
+        if K >= 512:
+            # few output tiles (the 64-row heads stream a whole weight matrix through 2..16 CTAs otherwise): split the
+            # reduction over K; partial tiles are added atomically, the first K range carries the bias
             sms = _sm_count()
             if tiles < sms:
                 split = max(1, min((2 * sms + tiles - 1) // tiles, K // 128))
@@ -249,7 +251,7 @@ def dropout_keep(shape, p: float, training: bool, device) -> Tuple[Optional[torc
     plumbing); the masking itself is fused into the consuming kernel."""
     if not training or p <= 0.0:
         return None, 1.0
-    keep = (torch.rand(shape, device=device) >= p).to(torch.uint8)
+    keep = torch.empty(shape, device=device, dtype=torch.uint8).bernoulli_(1.0 - p)      # one kernel, bytes straight away
     return keep, 1.0 / (1.0 - p)
 
 
