@@ -193,7 +193,9 @@ int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u
  *   64-bit word (order-preserving float bits << 32 | ~row-in-cloud) over all rows (max_u) and over rows with
  *   mask != 0 (max_m) -> max and FIRST argmax, bit-identical to a max over the stored tensor
  *   (models/PointNetEncoder.py:108-110, models/VertexPredictor.py:87).  Both outputs are [clouds, N] words the caller
- *   zeroes; a cloud = points_per_cloud (>= 32) consecutive rows, row_offset = global index of row 0 (chunked calls).
+ *   zeroes; a cloud = points_per_cloud (>= 32) consecutive rows, row_offset = global index of row 0 (chunked calls),
+ *   index_offset is added to the stored point index (clouds sharded by points across ranks: SURVEY 8e config 4; the
+ *   packed words of all ranks then combine with an integer MAX all-reduce).
  * wf_ln_relu_bf16_fwd_colsum: wf_ln_relu_bf16_fwd that also writes per-row-block column sums of h (all rows / valid
  *   rows) to `part` (wf_seg_part_floats(total_rows, C) floats); wf_seg_mean adds them in block order into
  *   hbar[2][B][C] = mean over all rows, mean over valid rows (sum / valid[b]).  The mean pools of the point features
@@ -201,8 +203,8 @@ int wf_pool_bwd(const float* g_max_m, const float* g_avg_m, const float* g_max_u
  *   with the mean).  points_per_cloud >= 128, row_offset % 128 == 0.
  * wf_pool_finalize: decodes the packed maxima, adds the bias: lin[2][B][C] = hbar W^T (no bias). */
 int wf_gemm_bf16_pool(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
-                      const float* bias, int points_per_cloud, int row_offset, const uint8_t* mask,
-                      uint64_t* max_u, uint64_t* max_m, wf_stream_t stream);
+                      const float* bias, int points_per_cloud, int row_offset, int index_offset,
+                      const uint8_t* mask, uint64_t* max_u, uint64_t* max_m, wf_stream_t stream);
 int wf_ln_relu_bf16_fwd_colsum(const void* z, const float* mean, const float* rstd,
                                const float* gamma, const float* beta, void* h, const uint8_t* mask,
                                int M, int C, int points_per_cloud, int row_offset, float* part,

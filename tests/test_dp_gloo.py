@@ -131,3 +131,57 @@ def test_shard_loss_weights_sum_rules():
     assert abs(sum(w[0] for w in ws) - 1.0) < 1e-12 and abs(sum(w[1] for w in ws) - 1.0) < 1e-12
     # edge: (B_r * maxE_r) / (B * maxE)
     assert abs(ws[0][2] - (4 * 21) / (6 * 28)) < 1e-12 and abs(ws[1][2] - (2 * 28) / (6 * 28)) < 1e-12
+
+
+def _pool_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wf_b200.parallel import reduce_pool_shards
+    g = torch.Generator().manual_seed(100 + rank)
+    B, C, K, n = 3, 16, 8, 50
+    vals = torch.randn(B, n, C, generator=g).clamp(max=2.5)
+    vals[:, 7] = 3.0                                        # a tie across ranks on the maximum: smallest GLOBAL index must win
+    mask = torch.rand(B, n, generator=g) > 0.3
+
+    def pack(v, idx):                                       # the kernels' packing (gemm_tc.cu pool_push), in numpy
+        import numpy as np
+        u = v.numpy().astype(np.float32).view(np.uint32).astype(np.uint64)
+        o = np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000)
+        return torch.from_numpy(((o << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - idx.numpy().astype(np.uint64))).astype(np.int64))
+    gidx = (torch.arange(n) + rank * n).view(1, n, 1).expand(B, n, C)
+    pk = pack(vals, gidx)
+    flip = -(1 << 63)                                       # unsigned order for torch's signed int64 max
+    pu = (pk ^ flip).max(dim=1).values ^ flip
+    pm = torch.where(mask.unsqueeze(-1), pk ^ flip, torch.full_like(pk, flip)).max(dim=1).values ^ flip
+    packed = torch.stack([pu, pm])
+    hsum = torch.stack([vals[..., :K].sum(1), (vals[..., :K] * mask.unsqueeze(-1)).sum(1)])
+    cnt = mask.sum(1).float()
+    reduce_pool_shards(packed, hsum, cnt)
+    q.put((rank, packed, hsum, cnt, vals, mask))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_point_sharded_pool_reduce_gloo():
+    """reduce_pool_shards over 2 gloo ranks: integer MAX of the packed (value, ~global index) words = global max with the
+    smallest global index on ties; sums and counts add."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    ps = [ctx.Process(target=_pool_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    [p.join(timeout=60) for p in ps]
+    allv = torch.cat([res[0][4], res[1][4]], dim=1); allm = torch.cat([res[0][5], res[1][5]], dim=1)
+    for r in range(2):
+        packed, hsum, cnt = res[r][1], res[r][2], res[r][3]
+        idx = (0xFFFFFFFF - (packed[0].numpy().astype(np.uint64) & np.uint64(0xFFFFFFFF))).astype(np.int64)
+        ref_max = allv.max(dim=1).values
+        first = torch.where(allv == ref_max.unsqueeze(1), torch.arange(allv.shape[1]).view(1, -1, 1), 10 ** 6).min(dim=1).values
+        assert np.array_equal(idx, first.numpy())
+        assert (first == 7).all()                           # the planted tie: rank 0's point 7 wins over rank 1's (global 57)
+        assert torch.allclose(hsum[0], allv[..., :8].sum(1), atol=1e-5)
+        assert torch.allclose(hsum[1], (allv[..., :8] * allm.unsqueeze(-1)).sum(1), atol=1e-5)
+        assert torch.equal(cnt, allm.sum(1).float())

@@ -421,3 +421,64 @@ def test_pool_fused_bwd_matches_dense(ops):
     assert_close(dW, dW_ref, 2e-5, "dW")
     # masked-avg term of db: the library's rule is "cloud has a valid point" (arg_m >= 0), the dense one sums the mask
     assert_close(db, db_ref, 2e-5, "db")
+
+
+def _enc_and_input(seed, B, N, pad):
+    from oracle import wireframe_oracle as wo
+    from models.PointNetEncoder import PointNetEncoder
+    torch.manual_seed(0)
+    enc = PointNetEncoder().cuda()
+    sd = {k[len("encoder."):]: v for k, v in wo.make_state_dict(seed, 16).items() if k.startswith("encoder.")}
+    enc.load_state_dict(sd)
+    x, _, _ = wo.make_inputs(seed + 1, B, N, 16, pad_frac=pad, norm_intensity=True)
+    return enc, x.cuda()
+
+
+def test_encoder_inference_chunked_is_bit_identical(ops):
+    """The no_grad encoder (chunked over points, three reused buffers) must return the same bits as the training forward:
+    same kernels per row, packed maxima are order-independent, column sums are added per 128-row block in block order."""
+    enc, x = _enc_and_input(9, 3, 1000, 0.1)
+    ops.set_precision("bf16")
+    ref = [t.detach().clone() for t in enc.pooled(x)[:6]]          # autograd path (grad enabled)
+    for chunk in (384, 1280, 1 << 19):
+        old = ops.INFER_CHUNK_ROWS
+        ops.INFER_CHUNK_ROWS = chunk
+        try:
+            with torch.no_grad():
+                out = enc.pooled(x)[:6]
+        finally:
+            ops.INFER_CHUNK_ROWS = old
+        for a, b, n in zip(out, ref, ("max_m", "avg_m", "max_u", "mean_u", "arg_m", "arg_u")):
+            assert torch.equal(a, b), f"chunk {chunk}: {n} differs"
+
+
+def test_encoder_point_sharded_matches_unsharded(ops):
+    """SURVEY 8e config 4 (batch < world): clouds split by points over 2 'ranks' (emulated on one device: the two shards'
+    partial pools are combined exactly as reduce_pool_shards' MAX / SUM all-reduces would).  Max pools and GLOBAL argmax
+    indices must be bit-identical to the unsharded encoder, mean pools equal to fp32 summation order."""
+    enc, x = _enc_and_input(4, 2, 1024, 0.1)
+    ops.set_precision("bf16")
+    with torch.no_grad():
+        ref = enc.pooled(x)[:6]
+    p = []
+    for li in range(4):
+        lin, ln = enc.mlp[4 * li], enc.mlp[4 * li + 1]
+        p += [lin.weight, lin.bias, ln.weight, ln.bias]
+    p += [enc.mlp[16].weight, enc.mlp[16].bias]
+    world, n = 2, 512
+    shards = [x[:, r * n:(r + 1) * n].contiguous() for r in range(world)]
+    stash = []
+    for r in range(world):                                   # pass 1: collect each rank's partial pools
+        ops.encoder_pooled_infer(shards[r], p, index_offset=r * n, points_total=world * n,
+                                 reduce_fn=lambda a, b, c: stash.append((a.clone(), b.clone(), c.clone())))
+    flip = -(1 << 63)                                        # the words are unsigned: compare in unsigned order
+    packed = torch.maximum(stash[0][0] ^ flip, stash[1][0] ^ flip) ^ flip; hsum = stash[0][1] + stash[1][1]; cnt = stash[0][2] + stash[1][2]
+
+    def fake_allreduce(a, b, c):
+        a.copy_(packed); b.copy_(hsum); c.copy_(cnt)
+    for r in range(world):                                   # pass 2: every rank finalises the combined pools
+        out = ops.encoder_pooled_infer(shards[r], p, index_offset=r * n, points_total=world * n, reduce_fn=fake_allreduce)
+        assert torch.equal(out[0], ref[0]) and torch.equal(out[4], ref[4]), "masked max / global argmax"
+        assert torch.equal(out[2], ref[2]) and torch.equal(out[5], ref[5]), "unmasked max / global argmax"
+        assert_close(out[1], ref[1], 1e-5, "masked mean pool")
+        assert_close(out[3], ref[3], 1e-5, "unmasked mean pool")

@@ -67,6 +67,15 @@ for e in ev:
     agg[n][0] += 1; agg[n][1] += e["dur"]
 print(f"{steps} steps: span {(t1 - t0) / 1e3 / steps:.2f} ms/step, GPU busy {busy / 1e3 / steps:.2f} ms/step, "
       f"idle {(t1 - t0 - busy) / 1e3 / steps:.2f} ms/step in {len(gaps) // steps} gaps/step")
+if len(sys.argv) > 2 and sys.argv[2] == "--seq":
+    # kernel sequence of the last step (from its first point_mask kernel)
+    starts = [i for i, e in enumerate(ev) if "point_mask" in e["name"]]
+    prev_end = None
+    for e in ev[starts[-1]:]:
+        n = re.sub(r"\(.*", "", e["name"]); n = re.sub(r"^void ", "", n).replace("at::native::", "at::")[:64]
+        gap = 0.0 if prev_end is None else e["ts"] - prev_end
+        print(f"{e['dur']:9.1f} us  gap {gap:6.1f}  {n}")
+        prev_end = e["ts"] + e["dur"]
 gaps.sort(reverse=True)
 print("largest gaps (us, kernel that followed):", [(round(g, 1), n) for g, n in gaps[:12]])
 for n, (c, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:

@@ -59,7 +59,8 @@ struct Params {
     // storing D, every column's maximum over the rows of each cloud (pool_n consecutive rows) goes to a packed
     // 64-bit atomicMax -- (order-preserving bits of the value << 32) | ~(row within the cloud) -- so ties resolve to the
     // first row, exactly like torch.max(dim=1).  pool_max_u: all rows; pool_max_m: rows with mask != 0.
-    int pool_n, pool_row0;              // points per cloud (0 = off); global row index of this launch's row 0
+    int pool_n, pool_row0, pool_idx0;   // points per cloud (0 = off); global row index of this launch's row 0; offset added to
+                                        // the stored point index (point-sharded clouds: this rank's first point)
     const uint8_t* pool_mask;
     unsigned long long* pool_max_u;
     unsigned long long* pool_max_m;
@@ -358,7 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                         if (col < p.N) {
                             const int b = pool_b0 + seg;
-                            const int base = p.pool_row0 + row0 - b * p.pool_n;            // row index inside the cloud of local row 0
+                            const int base = p.pool_idx0 + p.pool_row0 + row0 - b * p.pool_n;            // row index inside the cloud of local row 0
                             const size_t o = (size_t)b * p.N + col;
                             pool_push(p.pool_max_u + o, mu, (uint32_t)(base + au));
                             if (am >= 0) pool_push(p.pool_max_m + o, mm, (uint32_t)(base + am));
@@ -516,7 +517,7 @@ static int cluster_mode() {
     return v;
 }
 
-struct PoolArgs { int n, row0; const uint8_t* mask; unsigned long long* max_u; unsigned long long* max_m; };
+struct PoolArgs { int n, row0, idx0; const uint8_t* mask; unsigned long long* max_u; unsigned long long* max_m; };
 
 // esz 2: bf16 operands; esz 4: fp32 operands multiplied as tf32
 static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N, int K,
@@ -572,8 +573,8 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     p.kb_per_split = cdiv(p.nkb, split_k);
     p.split_k = cdiv(p.nkb, p.kb_per_split);
     p.bias = bias; p.D = D; p.ldd = ldd; p.out_dtype = out_dtype; p.accumulate = accumulate; p.rowstats = rowstats;
-    p.pool_n = 0; p.pool_row0 = 0; p.pool_mask = nullptr; p.pool_max_u = nullptr; p.pool_max_m = nullptr;
-    if (pool != nullptr) { p.pool_n = pool->n; p.pool_row0 = pool->row0; p.pool_mask = pool->mask; p.pool_max_u = pool->max_u; p.pool_max_m = pool->max_m; }
+    p.pool_n = 0; p.pool_row0 = 0; p.pool_idx0 = 0; p.pool_mask = nullptr; p.pool_max_u = nullptr; p.pool_max_m = nullptr;
+    if (pool != nullptr) { p.pool_n = pool->n; p.pool_row0 = pool->row0; p.pool_idx0 = pool->idx0; p.pool_mask = pool->mask; p.pool_max_u = pool->max_u; p.pool_max_m = pool->max_m; }
     long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
                                 : (long long)m_units * p.tiles_n * p.split_k;
     const int workers = (int)(items < workers_max ? items : workers_max);
@@ -603,12 +604,12 @@ extern "C" int wf_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B,
 extern "C" int wf_gemm_rowstats_parts(int N) { return 2 * wf::cdiv(N, wf::tc::BN); }
 
 extern "C" int wf_gemm_bf16_pool(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
-                                 int points_per_cloud, int row_offset, const uint8_t* mask, uint64_t* max_u,
-                                 uint64_t* max_m, wf_stream_t stream) {
-    WF_CHECK_ARG(points_per_cloud >= 32 && row_offset >= 0,
-                 "wf_gemm_bf16_pool: points_per_cloud must be >= 32 (got %d), row_offset >= 0", points_per_cloud);
+                                 int points_per_cloud, int row_offset, int index_offset, const uint8_t* mask,
+                                 uint64_t* max_u, uint64_t* max_m, wf_stream_t stream) {
+    WF_CHECK_ARG(points_per_cloud >= 32 && row_offset >= 0 && index_offset >= 0,
+                 "wf_gemm_bf16_pool: points_per_cloud must be >= 32 (got %d), row_offset/index_offset >= 0", points_per_cloud);
     WF_CHECK_ARG(max_u != nullptr && max_m != nullptr, "wf_gemm_bf16_pool: packed outputs required");
-    wf::tc::PoolArgs pa{points_per_cloud, row_offset, mask, reinterpret_cast<unsigned long long*>(max_u),
+    wf::tc::PoolArgs pa{points_per_cloud, row_offset, index_offset, mask, reinterpret_cast<unsigned long long*>(max_u),
                         reinterpret_cast<unsigned long long*>(max_m)};
     return wf::tc::gemm_tc(2, A, lda, 1, B, ldb, 1, M, N, K, bias, nullptr, 8, WF_BF16, 0, 1, nullptr, wf::as_stream(stream), &pa);
 }

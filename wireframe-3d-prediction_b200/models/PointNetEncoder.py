@@ -43,6 +43,10 @@ class PointNetEncoder(nn.Module):
                 p += [lin.weight, lin.bias, ln.weight, ln.bias]
             last = self.mlp[4 * self._n_hidden]
             p += [last.weight, last.bias]
+            if (not torch.is_grad_enabled() and not want_point_features and ops.FUSED_POOL
+                    and x.shape[1] >= ops._FUSED_MIN_POINTS):
+                # inference: chunked over points, nothing saved (evaluate.py:71 runs under torch.no_grad())
+                return (*ops.encoder_pooled_infer(x, p), None)
             r = ops.EncoderPointMLP_TC.apply(x, bool(want_point_features), *p)
             return (*r[:6], r[6] if want_point_features else None)
         B, N, D = x.shape

@@ -47,7 +47,7 @@ SIGNATURES = {
     "wf_cast_bf16": [P, I, I, P, I, P],
     "wf_pool_fwd": [P, P, P, I, I, I, P, P, P, P, P, P, P],
     "wf_pool_bwd": [P, P, P, P, P, P, P, P, I, I, I, P, I, P, P],
-    "wf_gemm_bf16_pool": [P, I, P, I, I, I, I, P, I, I, P, P, P, P],
+    "wf_gemm_bf16_pool": [P, I, P, I, I, I, I, P, I, I, I, P, P, P, P],
     "wf_ln_relu_bf16_fwd_colsum": [P, P, P, P, P, P, P, I, I, I, I, P, P],
     "wf_seg_part_floats": [I, I],
     "wf_seg_mean": [P, P, I, I, I, P, P],

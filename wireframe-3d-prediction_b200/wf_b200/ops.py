@@ -323,7 +323,7 @@ def gemm_bf16(A, B, *, M, N, K, kmajor=True, bias=None, out, accumulate=False, s
     return out
 
 
-def gemm_bf16_pool(A, Wb, *, M, N, K, bias, points_per_cloud, row_offset, mask, packed):
+def gemm_bf16_pool(A, Wb, *, M, N, K, bias, points_per_cloud, row_offset, mask, packed, index_offset=0):
     """Final per-point Linear whose epilogue max-pools instead of storing (wf_gemm_bf16_pool).  packed: int64 [2, clouds, N]
     (zero-initialised by the caller; [0] = all rows, [1] = valid rows)."""
     prof = GEMM_PROFILE
@@ -331,7 +331,7 @@ def gemm_bf16_pool(A, Wb, *, M, N, K, bias, points_per_cloud, row_offset, mask, 
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
     call("wf_gemm_bf16_pool", _p(A), A.stride(0), _p(Wb), Wb.stride(0), M, N, K, _p(bias), int(points_per_cloud),
-         int(row_offset), _p(mask), _p(packed[0]), _p(packed[1]), _s())
+         int(row_offset), int(index_offset), _p(mask), _p(packed[0]), _p(packed[1]), _s())
     if prof is not None:
         e1.record()
         prof.append((e0, e1, 2.0 * M * N * K))
@@ -349,6 +349,94 @@ def cast_bf16(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     call("wf_cast_bf16", _p(w), R, C, _p(out), int(transpose), _s())
     _count()
     return out
+
+
+INFER_CHUNK_ROWS = int(os.environ.get("WF_B200_INFER_CHUNK_ROWS", str(1 << 19)))
+
+
+def encoder_pooled_infer(x, params, *, chunk_rows=None, index_offset=0, points_total=None, reduce_fn=None):
+    """Inference form of EncoderPointMLP_TC (no autograd, nothing saved): the per-point MLP runs over row chunks of at most
+    `chunk_rows` points through three reused bf16 buffers, so a batch of million-point scans (BASELINE.json configs[3]:
+    8 x 1M points = 139 GB of training activations) needs ~2.5 KB/point of the largest chunk instead.  The pools accumulate
+    across chunks: packed maxima by atomicMax, column sums by row block (deterministic).
+
+    index_offset / points_total / reduce_fn: clouds sharded by POINTS across ranks (SURVEY 8e, config 4 with B < world):
+    this rank holds points [index_offset, index_offset + N) of every cloud out of points_total; reduce_fn(packed int64
+    [2,B,C], hsum fp32 [2,B,K], cnt fp32 [B]) combines the ranks' partial pools in place (wf_b200.parallel.reduce_pool_shards:
+    integer MAX and SUM all-reduces) before they are finalised.
+    Returns (max_m, avg_m, max_u, mean_u, arg_m, arg_u) like models/PointNetEncoder.py:103-111 + VertexPredictor.py:86-87."""
+    (W1, b1, g1, be1, W2, b2, g2, be2, W3, b3, g3, be3, W4, b4, g4, be4, W5, b5) = [t.detach() for t in params]
+    _need_cuda(x, W1)
+    x = _f32c(x.detach())
+    B, N, D = x.shape
+    M = B * N
+    dev = x.device
+    if N < _FUSED_MIN_POINTS:
+        raise _lib.WfError(f"encoder_pooled_infer needs >= {_FUSED_MIN_POINTS} points per cloud (got {N})")
+    chunk = INFER_CHUNK_ROWS if chunk_rows is None else int(chunk_rows)
+    chunk = max(128, (min(chunk, M) + 127) // 128 * 128)
+    mask, cnt = point_mask(x)                                  # cnt = max(#valid, 1)
+    layers = ((W2, b2, g2, be2), (W3, b3, g3, be3), (W4, b4, g4, be4))
+    wbs = [cast_bf16(W) for (W, _, _, _) in layers]
+    w5b = cast_bf16(W5)
+    C5, K5 = W5.shape
+    wmax = max(W.shape[0] for (W, _, _, _) in layers)
+    zbuf = torch.empty(chunk * wmax, device=dev, dtype=torch.bfloat16)
+    hbuf = [torch.empty(chunk * wmax, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    sbuf = torch.empty(call("wf_gemm_rowstats_parts", wmax) * chunk * 2, device=dev, dtype=torch.float32)
+    mean = torch.empty(chunk, device=dev, dtype=torch.float32)
+    rstd = torch.empty(chunk, device=dev, dtype=torch.float32)
+    part = torch.empty(call("wf_seg_part_floats", M, K5), device=dev, dtype=torch.float32)
+    packed = torch.zeros(2, B, C5, device=dev, dtype=torch.int64)
+    xf = x.view(M, D)
+    mflat = mask.view(M)
+    W1c = _f32c(W1)
+    for r0 in range(0, M, chunk):
+        m = min(chunk, M - r0)
+        h = hbuf[0][:m * W1.shape[0]].view(m, W1.shape[0])
+        call("wf_enc_l1_fwd", _p(xf[r0:]), _p(W1c), _p(b1), _p(g1), _p(be1), _p(h), BF16, m, D, W1.shape[0], 1e-5, _s())
+        _count()
+        cur = 0
+        for li, (W, b, g, be) in enumerate(layers):
+            Nn, K = W.shape
+            z = zbuf[:m * Nn].view(m, Nn)
+            parts = call("wf_gemm_rowstats_parts", Nn)
+            gemm_bf16(h, wbs[li], M=m, N=Nn, K=K, bias=b, out=z, rowstats=sbuf)
+            call("wf_stats_finalize", _p(sbuf), m, Nn, parts, 1e-5, _p(mean), _p(rstd), _s())
+            cur ^= 1
+            hn = hbuf[cur][:m * Nn].view(m, Nn)
+            if li == len(layers) - 1:
+                call("wf_ln_relu_bf16_fwd_colsum", _p(z), _p(mean), _p(rstd), _p(g), _p(be), _p(hn), _p(mflat[r0:]), m, Nn, N, r0,
+                     _p(part), _s())
+            else:
+                call("wf_ln_relu_bf16_fwd", _p(z), _p(mean), _p(rstd), _p(g), _p(be), _p(hn), m, Nn, _s())
+            _count(2)
+            h = hn
+        gemm_bf16_pool(h, w5b, M=m, N=C5, K=K5, bias=b5, points_per_cloud=N, row_offset=r0, mask=mflat[r0:], packed=packed,
+                       index_offset=index_offset)
+    hbar = torch.empty(2 * B, K5, device=dev, dtype=torch.float32)
+    ntot = N if points_total is None else int(points_total)
+    if reduce_fn is None:
+        call("wf_seg_mean", _p(part), _p(cnt), B, N, K5, _p(hbar), _s())
+        _count()
+    else:
+        ones = torch.ones(B, device=dev, dtype=torch.float32)
+        call("wf_seg_mean", _p(part), _p(ones), B, N, K5, _p(hbar), _s())     # hbar = [sum / N ; masked sum / 1]
+        _count()
+        hsum = hbar.view(2, B, K5)
+        hsum[0].mul_(float(N))                                 # back to plain sums; the division happens after the reduce
+        mk = mask.view(B, N).sum(dim=1, dtype=torch.float32)   # true valid counts of this shard (cnt is clamped to >= 1)
+        reduce_fn(packed, hsum, mk)
+        hsum[0].div_(float(ntot))
+        hsum[1].div_(mk.clamp_min(1.0).unsqueeze(1))
+    lin = gemm_f32(hbar, _f32c(W5), transB=True, tc=False)
+    mkt = lambda dt: torch.empty(B, C5, device=dev, dtype=dt)
+    max_m, avg_m, max_u, mean_u = mkt(torch.float32), mkt(torch.float32), mkt(torch.float32), mkt(torch.float32)
+    arg_m, arg_u = mkt(torch.int32), mkt(torch.int32)
+    call("wf_pool_finalize", _p(packed[0]), _p(packed[1]), _p(lin), _p(b5), B, C5, _p(max_m), _p(arg_m), _p(avg_m),
+         _p(max_u), _p(arg_u), _p(mean_u), _s())
+    _count()
+    return max_m, avg_m, max_u, mean_u, arg_m, arg_u
 
 
 class EncoderPointMLP_TC(torch.autograd.Function):

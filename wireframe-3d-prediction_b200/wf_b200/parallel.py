@@ -39,6 +39,44 @@ def shard_loss_weights(local_counts: Sequence[int], all_counts: Sequence[Sequenc
     return wv, wx, we
 
 
+_INT64_MIN = -(1 << 63)
+
+
+def reduce_pool_shards(packed: torch.Tensor, hsum: torch.Tensor, count: torch.Tensor, group=None) -> None:
+    """Combine per-rank partial pools of clouds that are sharded by POINTS (batch < world size).
+
+    packed : int64 [2, B, C]  order-preserving (value, ~point index) words of the max pools -> integer MAX all-reduce gives
+             the global max and, on ties, the smallest GLOBAL point index (ranks pass their first point as index_offset);
+    hsum   : fp32 [2, B, K]   column sums of the last hidden layer (all points / valid points) -> SUM;
+    count  : fp32 [B]         valid points of this shard -> SUM.
+    In place; a no-op without an initialised process group."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    # the words are UNSIGNED 64-bit; torch's int64 MAX is signed -> flip the top bit around the reduction
+    packed.bitwise_xor_(_INT64_MIN)
+    dist.all_reduce(packed, op=dist.ReduceOp.MAX, group=group)
+    packed.bitwise_xor_(_INT64_MIN)
+    dist.all_reduce(hsum, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+
+
+def encode_point_sharded(encoder, x_local: torch.Tensor, rank: int, world: int, group=None, chunk_rows=None):
+    """Encoder pools for clouds whose points are split across ranks: rank r holds points [r*n, (r+1)*n) of every cloud
+    (x_local: [B, n, 8]).  Every rank returns the pools of the FULL clouds (max_m, avg_m, max_u, mean_u, arg_m, arg_u);
+    argmax indices are global point indices.  One exchange: reduce_pool_shards (3 small all-reduces)."""
+    from . import ops
+    n = x_local.shape[1]
+    p = []
+    for li in range(encoder._n_hidden):
+        lin, ln = encoder.mlp[4 * li], encoder.mlp[4 * li + 1]
+        p += [lin.weight, lin.bias, ln.weight, ln.bias]
+    last = encoder.mlp[4 * encoder._n_hidden]
+    p += [last.weight, last.bias]
+    with torch.no_grad():
+        return ops.encoder_pooled_infer(x_local, p, chunk_rows=chunk_rows, index_offset=rank * n, points_total=world * n,
+                                        reduce_fn=lambda a, b, c: reduce_pool_shards(a, b, c, group))
+
+
 class GradAllReduce:
     """Bucketed, backward-overlapped gradient all-reduce (SUM) for a module replicated on every rank."""
 
