@@ -31,8 +31,17 @@ for p in (PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-# NCCL prints its version banner to STDOUT when NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line.
-os.environ["NCCL_DEBUG"] = "WARN"
+# stdout must carry exactly one JSON line, but libraries write there too (NCCL prints its version banner to stdout at
+# NCCL_DEBUG=VERSION and above): keep the real stdout aside and point fd 1 at stderr for the whole run.
+os.environ.pop("NCCL_DEBUG", None)
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import torch  # noqa: E402
 
@@ -166,7 +175,7 @@ def main_reference(args):
                                    f"{steps} steps after {warmup} warm-up, torch {torch.__version__} CPU, {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -311,7 +320,7 @@ def main_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"oracle port, 2 clouds x {POINTS} pts per step, 3 steps after 1 warm-up "
                                               f"({cms:.0f} ms/step), torch CPU {cores} threads"}
-        print(json.dumps(line), flush=True)
+        emit(line)
         print("per-step ms (device-resident):", step_ms[False], "\nper-step ms (e2e):", step_ms[True], file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()

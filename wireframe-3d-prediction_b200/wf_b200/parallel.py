@@ -4,10 +4,11 @@ One process per GPU (torch.distributed, NCCL over NVLink).  The batch of point c
 ranks; nothing in the model or the loss couples samples (LayerNorm is per row, pooling per cloud, matching
 per sample -- SURVEY 8e), so the only exchange is the gradient all-reduce:
 
-  * gradients live in ONE flat fp32 buffer (each `p.grad` is a view into it), cut into buckets in the order
-    the gradients become ready (edge head -> vertex head -> fusion -> encoder MLP);
-  * as soon as a bucket's last gradient has been accumulated, its all-reduce is issued on a side stream, so the
-    transfers (124 MB total) hide under the encoder backward, which is ~97 % of the backward time;
+  * parameters are cut into ~32 MB buckets in the order their gradients become ready (edge head -> vertex head ->
+    fusion -> encoder MLP); the gradient tensors themselves are reduced in place, grouped per bucket into one NCCL
+    launch (no flat staging buffer, no extra pass over the gradients);
+  * as soon as a bucket's last gradient exists, its all-reduce is issued on a side stream, so the transfers (124 MB
+    total) hide under the encoder backward, which is ~97 % of the backward time;
   * parameters that never receive a gradient (EdgePredictor.spatial_proj) keep `grad = None`, so the
     optimizer skips them exactly as in the reference.
 
@@ -78,39 +79,38 @@ def encode_point_sharded(encoder, x_local: torch.Tensor, rank: int, world: int, 
 
 
 class GradAllReduce:
-    """Bucketed, backward-overlapped gradient all-reduce (SUM) for a module replicated on every rank."""
+    """Bucketed, backward-overlapped gradient all-reduce (SUM) for a module replicated on every rank.
+
+    Zero-copy: every step starts from `grad = None` (train.py:138 zero_grad), autograd adopts the gradient tensors the
+    kernels return, and each bucket is reduced IN PLACE as one grouped NCCL launch over its tensors (ncclGroupStart/End
+    through torch's coalescing manager) -- no flat staging buffer, no copy or accumulate pass over the 124 MB."""
 
     def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20, process_group=None):
         self.module = module
         self.group = process_group
         self.bucket_bytes = bucket_bytes
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.flat: Optional[torch.Tensor] = None
         self.buckets: List[dict] = []
         self._order: List[torch.nn.Parameter] = []
         self._hooks = []
         self._handles = []
         self._stream = None
         self._built = False
+        self._bucket_of: Dict[torch.nn.Parameter, dict] = {}
         for p in module.parameters():
             if p.requires_grad:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     # ---- step protocol: zero() -> forward/backward -> finish() -> optimizer.step()
     def zero(self) -> None:
+        for p in self.module.parameters():
+            p.grad = None
         if self.world == 1:
-            # single process: nothing to reduce -- plain zero_grad(set_to_none=True) (train.py:138), autograd then adopts
-            # the kernels' gradient tensors instead of adding them into a flat buffer
-            for p in self.module.parameters():
-                p.grad = None
             return
         if self._built:
-            self.flat.zero_()
             for b in self.buckets:
                 b["pending"] = b["n"]
         else:
-            for p in self.module.parameters():
-                p.grad = None
             self._order = []
         self._handles = []
 
@@ -125,33 +125,45 @@ class GradAllReduce:
             return
         b["pending"] -= 1
         if b["pending"] == 0:
-            self._launch(b)
+            self._launch([q.grad for q in b["params"] if q.grad is not None])
 
-    def _launch(self, b: dict) -> None:
-        if self.world == 1:
+    def _reduce_list(self, tensors: List[torch.Tensor]) -> None:
+        """One grouped in-place SUM all-reduce over `tensors` (NCCL); per-tensor calls on backends without grouping."""
+        if not tensors:
             return
-        if self._stream is None:
-            self._stream = torch.cuda.Stream() if self.flat.is_cuda else None
-        if self._stream is not None:
-            self._stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self._stream):
-                self._handles.append(dist.all_reduce(b["view"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if tensors[0].is_cuda and hasattr(dist, "_coalescing_manager"):
+            with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self._handles.append(cm)
         else:
-            self._handles.append(dist.all_reduce(b["view"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for t in tensors:
+                self._handles.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _launch(self, tensors: List[torch.Tensor]) -> None:
+        if self.world == 1 or not tensors:
+            return
+        if tensors[0].is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream()
+            self._stream.wait_stream(torch.cuda.current_stream())       # the gradients were produced on the compute stream
+            with torch.cuda.stream(self._stream):
+                self._reduce_list(tensors)
+        else:
+            self._reduce_list(tensors)
 
     def finish(self) -> None:
-        """Call after backward().  First step: builds the flat buffer/buckets from the observed gradient order and
-        reduces everything at once; later steps: waits for the in-flight bucket reductions."""
+        """Call after backward().  First step: fixes the buckets from the observed gradient order and reduces everything
+        at once; later steps: waits for the in-flight bucket reductions."""
         if self.world == 1:
             return
         if not self._built:
             self._build()
-            if self.world > 1:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            return
-        for b in self.buckets:                      # a bucket whose hooks did not all fire (should not happen)
-            if b["pending"] > 0 and b["pending"] != b["n"]:
-                self._launch(b); b["pending"] = 0
+            self._launch([p.grad for b in self.buckets for p in b["params"]])
+        else:
+            for b in self.buckets:                  # a bucket whose hooks did not all fire (a parameter without gradient)
+                if 0 < b["pending"] < b["n"] or (b["pending"] == b["n"] and any(p.grad is not None for p in b["params"])):
+                    self._launch([q.grad for q in b["params"] if q.grad is not None]); b["pending"] = 0
         for h in self._handles:
             h.wait()
         if self._stream is not None:
@@ -159,31 +171,17 @@ class GradAllReduce:
         self._handles = []
 
     def _build(self) -> None:
-        params = [p for p in self._order if p.grad is not None]
         seen = set()
-        params = [p for p in params if not (id(p) in seen or seen.add(id(p)))]
-        total = sum(p.numel() for p in params)
-        dev = params[0].device
-        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
-        self._bucket_of: Dict[torch.nn.Parameter, dict] = {}
-        off = 0
-        cur = {"start": 0, "n": 0, "params": []}
+        params = [p for p in self._order if p.grad is not None and not (id(p) in seen or seen.add(id(p)))]
+        cur = {"n": 0, "params": [], "bytes": 0}
         for p in params:
-            n = p.numel()
-            view = self.flat[off:off + n].view_as(p)
-            view.copy_(p.grad)
-            p.grad = view
-            cur["params"].append(p); cur["n"] += 1
-            off += n
-            if (off - cur["start"]) * 4 >= self.bucket_bytes:
-                cur["end"] = off
+            cur["params"].append(p); cur["n"] += 1; cur["bytes"] += p.numel() * 4
+            if cur["bytes"] >= self.bucket_bytes:
                 self.buckets.append(cur)
-                cur = {"start": off, "n": 0, "params": []}
+                cur = {"n": 0, "params": [], "bytes": 0}
         if cur["n"]:
-            cur["end"] = off
             self.buckets.append(cur)
         for b in self.buckets:
-            b["view"] = self.flat[b["start"]:b["end"]]
             b["pending"] = b["n"]
             for p in b["params"]:
                 self._bucket_of[p] = b
