@@ -240,17 +240,34 @@ def main_gpu(args):
         torch.cuda.synchronize()
 
     step_ms = {False: [], True: []}
+    copy_stream = torch.cuda.Stream(dev)
+
+    def h2d():
+        """This step's inputs from pinned host memory, on the copy stream (overlaps the previous step's compute)."""
+        with torch.cuda.stream(copy_stream):
+            xin = x_pin.to(dev, non_blocking=True)
+            tg = {k: v.to(dev, non_blocking=True) for k, v in tgt_pin.items()}
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        return xin, tg, ev
 
     def timed(n, e2e):
+        """n steps, each bracketed by CUDA events, L2 flushed between steps (outside the events).  e2e: every step issues the
+        pinned host->device copy of the NEXT step's inputs inside its own timed region (side stream, as wf_b200.targets.
+        DevicePrefetcher does; the first step also pays for its own copy) and reads the loss back to the host."""
         total_ms = 0.0
-        for _ in range(n):
+        nxt = None
+        for i in range(n):
             flush.fill_(1)                                                  # L2 flush, outside the timed region
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:
-                xin = x_pin.to(dev, non_blocking=True)                      # H2D of this step's inputs (pinned)
-                tg = {k: v.to(dev, non_blocking=True) for k, v in tgt_pin.items()}
+                cur = nxt if nxt is not None else h2d()
+                nxt = h2d() if i + 1 < n else None
+                xin, tg, ev = cur
+                torch.cuda.current_stream().wait_event(ev)
+                for t in (xin, *tg.values()):
+                    t.record_stream(torch.cuda.current_stream())
                 step(xin, tg, True)                                         # D2H: the loss scalar
             else:
                 step(x, tgt, False)

@@ -229,6 +229,18 @@ int wf_pool_fused_bwd(const float* g_max_m, const float* g_avg_m, const float* g
 int wf_pool_fused_bwd_work_ints(int B, int C);
 
 /* ------------------------------------------------------------------------------------------
+ * Target preparation (train.py:48-88,112-115): ragged ground truth -> the four target tensors of
+ * WireframeLoss in ONE launch.  verts: all samples' vertices concatenated [T,3]; v_off[B+1]; edges: all samples' edges
+ * concatenated [total_edges,2] as float32 vertex indices (the dataset's dtype, datasets/building3d.py:180-183); e_off[B+1].
+ * Writes tgt_vertices [B,V,3] (zero padded), tgt_existence [B,V], counts [B] (int64, = len(vertices) per sample) and
+ * edge_labels [B,max_e]: label 1 at the row-major index of pair (min,max) among the pairs i<j<count
+ * (models/EdgePredictor.py:84-89 order), zero elsewhere; edges touching a vertex >= count, self loops and duplicates
+ * behave as in the reference's set lookup.  max_e = max_b count_b*(count_b-1)/2 (host-known). */
+int wf_pack_targets(const float* verts, const int32_t* v_off, const float* edges, const int32_t* e_off,
+                    int B, int V, int max_e, int total_edges, float* tgt_vertices, float* tgt_existence,
+                    int64_t* counts, float* edge_labels, wf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Edge head: ragged batch, vertices of all samples concatenated,
  * v_off[B+1] vertex prefix offsets, e_off[B+1] edge prefix offsets (int64), T = v_off[B]
  * (the host mirror knows T: counts are an input in training and one D2H read in inference).

@@ -211,6 +211,24 @@ def config5(quick):
         torch.cuda.empty_cache()
 
 
+def config_prep(quick):
+    """target preparation for a batch (train.py:48-88,112-115) -- device kernel vs the Python loops."""
+    from oracle import targets_oracle as to
+    from wf_b200.targets import prepare_targets
+    for B in ((64,) if quick else (64, 512)):
+        verts, edges = to.make_case(5, B, 64, min_c=16)
+        prepare_targets(verts, edges, 64, "cuda"); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            got = prepare_targets(verts, edges, 64, "cuda")
+        torch.cuda.synchronize()
+        gpu_ms = (time.perf_counter() - t0) / 10 * 1e3
+        t0 = time.perf_counter(); ref = to.prepare_targets(verts, edges, 64); cpu_ms = (time.perf_counter() - t0) * 1e3
+        same = all(torch.equal(got[k].cpu(), ref[k]) for k in ref)
+        out({"config": f"prep: targets for a batch of {B} (V=64, counts~U{{16..64}})", "device_path_ms_host_timed": gpu_ms,
+             "reference_python_loops_ms": cpu_ms, "identical": bool(same), "batches_per_s_device_path": 1e3 / gpu_ms})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="all")
@@ -226,3 +244,5 @@ if __name__ == "__main__":
         config4(a.quick)
     if a.config in ("5", "all"):
         config5(a.quick)
+    if a.config in ("prep", "all"):
+        config_prep(a.quick)

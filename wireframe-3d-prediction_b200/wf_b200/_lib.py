@@ -54,6 +54,7 @@ SIGNATURES = {
     "wf_pool_finalize": [P, P, P, P, I, I, P, P, P, P, P, P, P],
     "wf_pool_fused_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P],
     "wf_pool_fused_bwd_work_ints": [I, I],
+    "wf_pack_targets": [P, P, P, P, I, I, I, I, P, P, P, P, P],
     "wf_gather_prefix": [P, I, I, P, I, P, P],
     "wf_scatter_prefix_add": [P, I, I, P, I, P, P],
     "wf_attn_fwd": [P, P, P, I, I, I, I, P, P, P, F, P],
