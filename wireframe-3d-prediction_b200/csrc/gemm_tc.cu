@@ -315,17 +315,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (col0 >= p.N) break;                          // warp-uniform
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+                const bool full = col0 + 32 <= p.N;
+                float4 bb[8];                                    // bias requested before waiting for the accumulators
+                if (add_bias && full && bias_v4) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                }
                 ptx::tmem_ld_wait();
                 float v[32];
-                const bool full = col0 + 32 <= p.N;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if (add_bias) {
                     if (full && bias_v4) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        for (int j = 0; j < 8; ++j) {
+                            v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w;
                         }
                     } else {
 #pragma unroll
