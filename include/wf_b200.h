@@ -156,6 +156,14 @@ int wf_gemm_tf32(const float* A, int lda, int a_kmajor, const float* B, int ldb,
                  int N, int K, const float* bias, float* D, int ldd, int accumulate, int split_k,
                  wf_stream_t stream);
 
+/* wf_gemm_tf32 with a DETERMINISTIC split-K: each K range stores its partial tile into its own [M,N] fp32 slice of `work`
+ * (work_floats >= split_k * M * N), a second kernel adds the slices in order (+ bias, + D when accumulate != 0).  Used for
+ * the forward and dX products of the 64-row heads, which have too few output tiles to fill the GPU but must stay
+ * bit-reproducible (only weight gradients use the atomic split-K).  N % 4 == 0. */
+int wf_gemm_tf32_splitk(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor,
+                        int M, int N, int K, const float* bias, float* D, int ldd, int accumulate,
+                        int split_k, float* work, int64_t work_floats, wf_stream_t stream);
+
 /* bf16 LayerNorm+ReLU passes between the tensor-core layers (models/PointNetEncoder.py:38-39), 16-byte vectorised,
  * HBM-bound.  fwd: h = relu(LN(z)) with the row statistics from the GEMM epilogue.  bwd: dz from dh and z in ONE pass;
  * dgamma/dbeta/dcolsum (the Linear's bias gradient) are accumulated (caller zeroes).  C in {512,1024,2048}. */

@@ -482,3 +482,23 @@ def test_encoder_point_sharded_matches_unsharded(ops):
         assert torch.equal(out[2], ref[2]) and torch.equal(out[5], ref[5]), "unmasked max / global argmax"
         assert_close(out[1], ref[1], 1e-5, "masked mean pool")
         assert_close(out[3], ref[3], 1e-5, "unmasked mean pool")
+
+
+@pytest.mark.parametrize("M,N,K,tB", [(64, 2048, 4096, True), (64, 512, 4096, False), (64, 4096, 512, True), (100, 1024, 2048, True)])
+def test_tf32_split_k_forward_is_deterministic(ops, M, N, K, tB):
+    """Few-tile TF32 products (the 64-row heads) split the reduction over K; forward/dX products must stay bit-reproducible:
+    partial tiles go to workspace slices that are added in a fixed order (wf_gemm_tf32_splitk)."""
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda") / math.sqrt(K) if tB else torch.randn(K, N, device="cuda") / math.sqrt(K)
+    bias = torch.randn(N, device="cuda")
+    ops.set_precision("bf16")
+    l0 = ops.LAUNCHES
+    outs = [ops.gemm_f32(A, B, transB=tB, bias=bias) for _ in range(3)]
+    assert ops.LAUNCHES - l0 == 6, "expected the split-K pair of launches (GEMM + ordered reduction)"
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = A.double() @ (B.double().t() if tB else B.double()) + bias.double()
+    assert_close(outs[0], ref, 2e-3, "tf32 split-K product")
+    acc = outs[0].clone()
+    ops.gemm_f32(A, B, transB=tB, out=acc, beta=1.0)
+    assert_close(acc, 2 * ref - bias.double(), 2e-3, "tf32 split-K accumulate (beta = 1)")

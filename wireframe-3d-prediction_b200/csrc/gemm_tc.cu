@@ -54,6 +54,7 @@ struct Params {
     const float* bias;
     void* D;
     int ldd, out_dtype, accumulate;
+    long long split_stride;      // > 0: split s stores (not adds) its partial tile at D + s * split_stride (deterministic split-K)
     float* rowstats;
     // pool mode (final encoder Linear, models/PointNetEncoder.py:94,103-111 + models/VertexPredictor.py:87): instead of
     // storing D, every column's maximum over the rows of each cloud (pool_n consecutive rows) goes to a packed
@@ -308,6 +309,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const bool add_bias = p.bias != nullptr && kb0 == 0;       // split-K: the first K range carries the bias
+            // deterministic split-K: every K range has its own fp32 slice of the workspace, summed in order afterwards
+            void* const Dt = p.split_stride > 0 ? static_cast<void*>(static_cast<float*>(p.D) + (long long)(kb0 / p.kb_per_split) * p.split_stride)
+                                                : p.D;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
             for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
@@ -389,7 +393,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
                                 pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
                                 pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + (size_t)(row0 + rl) * p.ldd + col0 + cc) = pk;
+                                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(Dt) + (size_t)(row0 + rl) * p.ldd + col0 + cc) = pk;
                             }
                         }
                     } else {
@@ -399,19 +403,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const int rl = rr + 4 * i;
                             const float4 a = *reinterpret_cast<const float4*>(stg + stg_v4(rl, cc >> 2));
                             if (row0 + rl < p.M)
-                                *reinterpret_cast<float4*>(static_cast<float*>(p.D) + (size_t)(row0 + rl) * p.ldd + col0 + cc) = a;
+                                *reinterpret_cast<float4*>(static_cast<float*>(Dt) + (size_t)(row0 + rl) * p.ldd + col0 + cc) = a;
                         }
                     }
                     __syncwarp();
                 } else if (row_ok) {
                     // ---- column tail or split-K accumulation: direct per-row access
                     if (p.out_dtype == WF_BF16) {
-                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(Dt) + (size_t)row * p.ldd + col0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)                      // static indices: keeps v[] in registers
                             if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
                     } else {
-                        float* dst = static_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+                        float* dst = static_cast<float*>(Dt) + (size_t)row * p.ldd + col0;
                         if (p.accumulate) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
@@ -440,6 +444,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     if (CL) ptx::cluster_sync();                 // nobody exits while the peer may still write our smem / barriers
     if (warp == 2) { if (TWO) ptx::tmem_dealloc2(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// out[m][n] = bias[n] + sum_s part[s][m][n], s in order: the second half of the deterministic split-K
+__global__ void splitk_reduce_kernel(const float4* __restrict__ part, int split, long long mn4, int n4, const float4* __restrict__ bias,
+                                     float* __restrict__ out, int ldo, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < mn4; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / n4; const int c4 = (int)(i - m * n4);
+        float4 a = bias ? bias[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < split; ++s) { const float4 t = part[(long long)s * mn4 + i]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        float4* dst = reinterpret_cast<float4*>(out + m * ldo + 4 * c4);
+        if (accumulate) { const float4 o = *dst; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+        *dst = a;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -526,7 +543,7 @@ struct PoolArgs { int n, row0, idx0; const uint8_t* mask; unsigned long long* ma
 // esz 2: bf16 operands; esz 4: fp32 operands multiplied as tf32
 static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N, int K,
                    const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k, float* rowstats,
-                   cudaStream_t stream, const PoolArgs* pool = nullptr) {
+                   cudaStream_t stream, const PoolArgs* pool = nullptr, float* det_work = nullptr, long long det_work_floats = 0) {
     const int al = 16 / esz;                                     // elements per 16 bytes
     WF_CHECK_ARG(M > 0 && N > 0 && K > 0, "wf_gemm_tc: empty problem M=%d N=%d K=%d", M, N, K);
     WF_CHECK_ARG(lda % al == 0 && ldb % al == 0, "wf_gemm_tc: lda/ldb must be multiples of %d elements (16-byte TMA strides)", al);
@@ -538,7 +555,7 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     WF_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "wf_gemm_tc: D must be 16-byte aligned");
     WF_CHECK_ARG(pool != nullptr || D != nullptr, "wf_gemm_tc: D is null");
     if (split_k < 1) split_k = 1;
-    WF_CHECK_ARG(split_k == 1 || accumulate, "wf_gemm_tc: split_k > 1 needs accumulate");
+    WF_CHECK_ARG(split_k == 1 || accumulate || det_work != nullptr, "wf_gemm_tc: split_k > 1 needs accumulate or a workspace");
     const int BKe = 128 / esz, mnbox = 128 / esz;
     CUtensorMap ma, mb;
     int rc;
@@ -563,7 +580,8 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
         // item count fills whole waves of workers (>= 95 %), which is what removes the wave-quantisation loss.
         const long long tiles = (long long)m_units * p.tiles_n;
         int best = 1; double best_eff = 0.0;
-        const int smax = p.nkb / 4 < 64 ? (p.nkb / 4 < 1 ? 1 : p.nkb / 4) : 64;
+        int smax = p.nkb / 4 < 64 ? (p.nkb / 4 < 1 ? 1 : p.nkb / 4) : 64;
+        if (det_work != nullptr && smax > split_k) smax = split_k;       // the caller sized the workspace for its own split count
         for (int sp = 1; sp <= smax; ++sp) {
             const long long it = tiles * sp;
             const long long waves = (it + workers_max - 1) / workers_max;
@@ -577,6 +595,18 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     p.kb_per_split = cdiv(p.nkb, split_k);
     p.split_k = cdiv(p.nkb, p.kb_per_split);
     p.bias = bias; p.D = D; p.ldd = ldd; p.out_dtype = out_dtype; p.accumulate = accumulate; p.rowstats = rowstats;
+    p.split_stride = 0;
+    const bool det = det_work != nullptr && p.split_k > 1;
+    if (det) {
+        // deterministic split-K: partial tiles go to [split][M][N] fp32 slices of the workspace, splitk_reduce_kernel adds them
+        WF_CHECK_ARG(out_dtype == WF_F32 && N % 4 == 0 && ldd % 4 == 0 && rowstats == nullptr && pool == nullptr,
+                     "wf_gemm_tc: deterministic split-K needs an fp32 output with N %% 4 == 0");
+        WF_CHECK_ARG((long long)p.split_k * M * N <= det_work_floats,
+                     "wf_gemm_tc: split-K workspace too small (%lld floats needed)", (long long)p.split_k * M * N);
+        WF_CHECK_ARG((reinterpret_cast<uintptr_t>(det_work) & 15) == 0 && (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+                     "wf_gemm_tc: workspace / bias alignment");
+        p.bias = nullptr; p.D = det_work; p.ldd = N; p.accumulate = 0; p.split_stride = (long long)M * N;
+    }
     p.pool_n = 0; p.pool_row0 = 0; p.pool_idx0 = 0; p.pool_mask = nullptr; p.pool_max_u = nullptr; p.pool_max_m = nullptr;
     if (pool != nullptr) { p.pool_n = pool->n; p.pool_row0 = pool->row0; p.pool_idx0 = pool->idx0; p.pool_mask = pool->mask; p.pool_max_u = pool->max_u; p.pool_max_m = pool->max_m; }
     long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
@@ -585,15 +615,22 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     const int grid = mc ? 2 * workers : workers;
     const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
     switch (key) {
-        case 3: return launch_mc<2, true, true>(mode, ma, mb, p, grid, stream);
-        case 2: return launch_mc<2, true, false>(mode, ma, mb, p, grid, stream);
-        case 1: return launch_mc<2, false, true>(mode, ma, mb, p, grid, stream);
-        case 0: return launch_mc<2, false, false>(mode, ma, mb, p, grid, stream);
-        case 7: return launch_mc<4, true, true>(mode, ma, mb, p, grid, stream);
-        case 6: return launch_mc<4, true, false>(mode, ma, mb, p, grid, stream);
-        case 5: return launch_mc<4, false, true>(mode, ma, mb, p, grid, stream);
-        default: return launch_mc<4, false, false>(mode, ma, mb, p, grid, stream);
+        case 3: rc = launch_mc<2, true, true>(mode, ma, mb, p, grid, stream); break;
+        case 2: rc = launch_mc<2, true, false>(mode, ma, mb, p, grid, stream); break;
+        case 1: rc = launch_mc<2, false, true>(mode, ma, mb, p, grid, stream); break;
+        case 0: rc = launch_mc<2, false, false>(mode, ma, mb, p, grid, stream); break;
+        case 7: rc = launch_mc<4, true, true>(mode, ma, mb, p, grid, stream); break;
+        case 6: rc = launch_mc<4, true, false>(mode, ma, mb, p, grid, stream); break;
+        case 5: rc = launch_mc<4, false, true>(mode, ma, mb, p, grid, stream); break;
+        default: rc = launch_mc<4, false, false>(mode, ma, mb, p, grid, stream); break;
     }
+    if (rc != WF_OK || !det) return rc;
+    const long long mn4 = (long long)M * N / 4;
+    const int rgrid = (int)(cdiv(mn4, 256) < 8LL * sm_count() ? cdiv(mn4, 256) : 8LL * sm_count());
+    splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(reinterpret_cast<const float4*>(det_work), p.split_k, mn4, N / 4,
+                                                    reinterpret_cast<const float4*>(bias), static_cast<float*>(D), ldd, accumulate);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
 }
 
 }}  // namespace wf::tc
@@ -622,4 +659,12 @@ extern "C" int wf_gemm_tf32(const float* A, int lda, int a_kmajor, const float* 
                             int K, const float* bias, float* D, int ldd, int accumulate, int split_k, wf_stream_t stream) {
     return wf::tc::gemm_tc(4, A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias, D, ldd, WF_F32, accumulate, split_k,
                            nullptr, wf::as_stream(stream));
+}
+
+extern "C" int wf_gemm_tf32_splitk(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, int M, int N,
+                                   int K, const float* bias, float* D, int ldd, int accumulate, int split_k, float* work,
+                                   int64_t work_floats, wf_stream_t stream) {
+    WF_CHECK_ARG(work != nullptr && work_floats >= 0, "wf_gemm_tf32_splitk: workspace required");
+    return wf::tc::gemm_tc(4, A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias, D, ldd, WF_F32, accumulate, split_k,
+                           nullptr, wf::as_stream(stream), nullptr, work, work_floats);
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "wf_enc_l1_bwd": [P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, F, P],
     "wf_gemm_bf16": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, I, P, P],
     "wf_gemm_tf32": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, P],
+    "wf_gemm_tf32_splitk": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, P, L, P],
     "wf_ln_relu_bf16_fwd": [P, P, P, P, P, P, I, I, P],
     "wf_ln_relu_bf16_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
     "wf_stats_finalize": [P, I, I, I, F, P, P, P],

@@ -108,10 +108,23 @@ def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0,
         split = 1
         if K >= 512:
             # few output tiles (the 64-row heads stream a whole weight matrix through 2..16 CTAs otherwise): split the
-            # reduction over K; partial tiles are added atomically, the first K range carries the bias
+            # reduction over K
             sms = _sm_count()
             if tiles < sms:
                 split = max(1, min((2 * sms + tiles - 1) // tiles, K // 128))
+        if split > 1 and not transA and N % 4 == 0:
+            # forward / dX products: deterministic split-K (partials in a workspace, added in order) -- the forward pass stays
+            # bit-reproducible; only weight gradients (transA) use the atomic variant below
+            acc = out is not None and beta == 1.0
+            if out is None:
+                out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+            work = torch.empty(split * M * N, device=A.device, dtype=torch.float32)
+            call("wf_gemm_tf32_splitk", _p(A), A.stride(0), int(not transA), _p(B), B.stride(0), int(transB), M, N, K, _p(bias),
+                 _p(out), out.stride(0), int(acc), int(split), _p(work), work.numel(), _s())
+            _count(2)
+            return out
+        if split > 1 and bias is not None:
+            split = 1
         accumulate = split > 1 or (out is not None and beta == 1.0)
         if out is None:
             out = (torch.zeros if accumulate else torch.empty)(M, N, device=A.device, dtype=torch.float32)
