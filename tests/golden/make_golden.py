@@ -179,3 +179,52 @@ if __name__ == "__main__":
     case_eval("eval_b2_n256_v16", seed=11, B=2, N=256, V=16)
     case_matchers("matchers", seed=13)
     case_loss_ties("loss_ties", seed=17)
+
+
+def case_real_building(name, seed, index=0):
+    """BASELINE.json configs[0] / SURVEY 8d config 1: a REAL building from the shipped dataset, read by the reference's own
+    loader (datasets/building3d.py: np.loadtxt, RGBA/256, centring + unit max-norm, 2560-point resampling; intensity stays
+    un-normalised), targets built as train.py:48-88,112-115 does, one training step of the unmodified reference with
+    the deterministic weights.  The loader's output (points, vertices, edges) is stored too -- it cannot regenerate from a seed."""
+    import yaml
+    from datasets import build_dataset
+    from oracle import targets_oracle as to
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    cfg = Cfg(yaml.safe_load(open(os.path.join(REF, "datasets", "dataset_config.yaml")))["Building3D"])
+    cfg["root_dir"] = os.path.join(REF, "datasets")
+    cfg["augment"] = False
+    np.random.seed(seed)                                   # random_sampling draws with the global numpy RNG
+    ds = build_dataset(cfg)["train"]
+    ds.pc_files.sort(); ds.wireframe_files.sort()
+    batch = ds.collate_batch([ds[index]])
+    x = batch["point_clouds"].float()                      # (1, 2560, 8), train.py:48
+    wf_v, wf_e = batch["wf_vertices"], batch["wf_edges"]
+    V = 38                                                 # the dataset's largest vertex count (SURVEY A.1)
+    from models.utils import create_edge_labels_from_edge_set
+    tgt = to.prepare_targets(wf_v, wf_e, V, label_fn=create_edge_labels_from_edge_set)
+    counts = tgt["vertex_counts"]
+    m, _ = build_reference(seed, V, True)
+    crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)
+    pred = m(x, counts)
+    matched = crit._hungarian_matching(pred, tgt)
+    ld = crit(pred, tgt)
+    ld["total_loss"].backward()
+    out = {
+        "meta": np.array([seed, 1, x.shape[1], V], np.int64),
+        "x": x.numpy(), "wf_vertices": wf_v[0].numpy(), "wf_edges": wf_e[0].numpy(),
+        "tgt_vertices": tgt["vertices"].numpy(), "tgt_existence": tgt["vertex_existence"].numpy(),
+        "tgt_edge_labels": tgt["edge_labels"].numpy(), "tgt_counts": counts.numpy(),
+        "vertices": pred["vertices"].detach().numpy(), "existence": pred["existence_probabilities"].detach().numpy(),
+        "edge_probs": pred["edge_probs"].detach().numpy(), "global_features": pred["global_features"].detach().numpy(),
+        "losses": np.array([ld[k].item() for k in ("total_loss", "vertex_loss", "existence_loss", "edge_loss")], np.float64),
+        "match_p": np.asarray(matched[0][0], np.int64), "match_t": np.asarray(matched[0][1], np.int64),
+    }
+    out.update(grad_digest(m.named_parameters()))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "points", tuple(x.shape), "vertices", int(counts[0]), "edges", len(wf_e[0]), "losses", out["losses"])
+
+
+if __name__ == "__main__" and os.environ.get("WF_GOLDEN_REAL", "1") == "1":
+    case_real_building("real_b1_n2560_v38", seed=19)

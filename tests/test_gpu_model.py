@@ -238,3 +238,60 @@ def test_loss_raises_scipy_errors_immediately_or_deferred():
     with pytest.raises(ValueError, match="invalid numeric"):
         crit.check_pending()
     crit(good, tgt); crit.check_pending()            # clean
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_real_building_vs_reference_golden(golden_dir, prec):
+    """BASELINE.json configs[0] / SURVEY 8d config 1: a REAL building as the reference's loader delivers it (2560 points,
+    RGBA/256, un-normalised intensity ~5e4), targets prepared ON THE DEVICE (wf_pack_targets), one training step through the
+    drop-in modules -- against the unmodified reference's outputs, losses, matching and all gradient norms."""
+    from wf_b200 import ops
+    from wf_b200.targets import prepare_targets
+    from losses.WireframeLoss import WireframeLoss
+    g = dict(np.load(os.path.join(golden_dir, "real_b1_n2560_v38.npz")))
+    seed, B, N, V = [int(v) for v in g["meta"]]
+    ops.set_precision(prec)
+    try:
+        m = _model(seed, V, True)
+        tgt = prepare_targets([torch.from_numpy(g["wf_vertices"])], [torch.from_numpy(g["wf_edges"])], V, "cuda")
+        assert np.array_equal(tgt["edge_labels"].cpu().numpy(), g["tgt_edge_labels"])
+        assert np.array_equal(tgt["vertices"].cpu().numpy(), g["tgt_vertices"])
+        assert np.array_equal(tgt["vertex_existence"].cpu().numpy(), g["tgt_existence"])
+        assert np.array_equal(tgt["vertex_counts"].cpu().numpy(), g["tgt_counts"])
+        x = torch.from_numpy(g["x"]).cuda()
+        pred = m(x, tgt["vertex_counts"])
+        crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)
+        ld = crit(pred, tgt)
+        ld["total_loss"].backward()
+        otol, gtol = (5e-4, 5e-3) if prec == "fp32" else (5e-2, 2.5e-1)
+        assert_close(pred["vertices"], torch.from_numpy(g["vertices"]), otol, "vertices")
+        assert_close(pred["existence_probabilities"], torch.from_numpy(g["existence"]), otol, "existence")
+        assert_close(pred["edge_probs"], torch.from_numpy(g["edge_probs"]), otol, "edge_probs")
+        assert_close(pred["global_features"], torch.from_numpy(g["global_features"]), otol, "global_features")
+        got = np.array([ld[k].item() for k in ("total_loss", "vertex_loss", "existence_loss", "edge_loss")])
+        np.testing.assert_allclose(got[2:], g["losses"][2:], rtol=otol * 5, atol=otol)
+        # With random-init weights the 38 predicted vertices of this building are nearly coincident, so many assignment
+        # costs are tied to ~1e-4 and the optimal matching is not stable under fp32 summation-order noise (raw intensity,
+        # SURVEY D6): the vertex term is compared loosely, and the matching against the oracle's solver on OUR predictions
+        # (same input -> must be identical, like tests/test_gpu_simt.py holds the solver to scipy).
+        np.testing.assert_allclose(got[:2], g["losses"][:2], rtol=5e-2)
+        from oracle import wireframe_oracle as wo
+        pred_cpu = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in pred.items()}
+        ref_match = wo.loss_matching(pred_cpu, {k: v.cpu() for k, v in tgt.items()})[0]
+        pi, ti = crit._hungarian_matching(pred, tgt)[0]
+        assert np.array_equal(pi, ref_match[0]) and np.array_equal(ti, ref_match[1])
+        fails = []
+        for k, p in m.named_parameters():
+            if "gnone/" + k in g:
+                assert p.grad is None, k
+                continue
+            ref_norm = float(g["gnorm/" + k][0])
+            e = abs(float(p.grad.double().norm()) - ref_norm) / max(ref_norm, 1e-12)
+            # raw intensity: the first LayerNorm's backward is ill-conditioned in fp32 (in the reference too); a different
+            # (equally optimal within noise) matching changes the vertex-term gradients of the heads
+            loose = 30.0 if k.startswith("encoder.mlp.0.") else (10.0 if prec == "fp32" else 1.0)
+            if e > gtol * loose:
+                fails.append((k, e))
+        assert not fails, f"{prec} gradient-norm mismatches: {fails[:6]}"
+    finally:
+        ops.set_precision("bf16")

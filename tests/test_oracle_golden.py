@@ -112,3 +112,29 @@ def test_loss_ties_match_reference(golden_dir):
 
 def test_golden_files_present(golden_dir):
     assert len(glob.glob(os.path.join(golden_dir, "*.npz"))) >= 6
+
+
+def test_real_building_matches_reference(golden_dir):
+    """BASELINE.json configs[0]: a real building of the shipped dataset as the reference's loader delivers it (2560 points,
+    un-normalised intensity), targets as train.py builds them, one training step -- oracle vs the unmodified reference."""
+    from oracle import targets_oracle as to
+    g = _load(golden_dir, "real_b1_n2560_v38")
+    seed, B, N, V = [int(v) for v in g["meta"]]
+    wf_v, wf_e = [torch.from_numpy(g["wf_vertices"])], [torch.from_numpy(g["wf_edges"])]
+    tgt = to.prepare_targets(wf_v, wf_e, V)
+    assert np.array_equal(tgt["edge_labels"].numpy(), g["tgt_edge_labels"]) and np.array_equal(tgt["vertices"].numpy(), g["tgt_vertices"])
+    assert np.array_equal(tgt["vertex_counts"].numpy(), g["tgt_counts"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in wo.make_state_dict(seed, V).items()}
+    ld, pred = wo.train_step(sd, torch.from_numpy(g["x"]), tgt, max_vertices=V)
+    tol = dict(rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(pred["vertices"].detach().numpy(), g["vertices"], **tol)
+    np.testing.assert_allclose(pred["edge_probs"].detach().numpy(), g["edge_probs"], **tol)
+    got = np.array([ld[k].item() for k in ("total_loss", "vertex_loss", "existence_loss", "edge_loss")])
+    np.testing.assert_allclose(got, g["losses"], rtol=1e-5, atol=1e-6)
+    pi, ti = wo.loss_matching(pred, tgt)[0]
+    assert np.array_equal(pi, g["match_p"]) and np.array_equal(ti, g["match_t"])
+    for k, p in sd.items():
+        if "gnone/" + k in g:
+            continue
+        ref_norm = g["gnorm/" + k][0]
+        assert abs(p.grad.double().norm().item() - ref_norm) <= 5e-3 * ref_norm + 1e-7, k
