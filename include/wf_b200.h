@@ -310,6 +310,37 @@ int wf_loss_bwd(const float* g_out, const float* pred_v, const float* pred_e, co
                 int Vt, int Ep, int El, float w_vertex, float w_edge, float w_exist, float* d_pred_v,
                 float* d_pred_e, float* d_edge_p, wf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Evaluation post-processing (eval/ap_calculator.py, called from evaluate.py:110).
+ * fp64 like numpy/scipy, ragged batches: sample b owns rows off[b]..off[b+1] of each input.
+ * ---------------------------------------------------------------------------------------- */
+
+/* eval/ap_calculator.py:8-36 hausdorff_distance_line.  Lines are (L,2,3) doubles holding
+ * [start, end-start] (the difference is formed by the host in the segments' own dtype, as numpy does
+ * at :24-25); weights[samples] = np.linspace(0,1,samples).  Block b of `out` (at out_off[b], row-major
+ * n_pred_b x n_tgt_b) = max(h(pred->tgt), h(tgt->pred)) over the sampled points; bit-equal to the
+ * reference's cdist/min/max chain.  max_p = max_b n_pred_b. */
+int wf_hausdorff_lines(const double* p_lines, const int64_t* p_off, const double* t_lines,
+                       const int64_t* t_off, const int64_t* out_off, int B, int max_p,
+                       const double* weights, int samples, double* out, wf_stream_t stream);
+
+/* scipy.spatial.distance.cdist(a_b, b_b) ('euclidean', double) per sample
+ * (eval/ap_calculator.py:45,192,225,249); max_block = max_b n_a*n_b. */
+int wf_cdist_f64(const double* a, const int64_t* a_off, const double* b, const int64_t* b_off,
+                 const int64_t* out_off, int B, int64_t max_block, int dim, double* out,
+                 wf_stream_t stream);
+
+/* scipy.optimize.linear_sum_assignment on B fp64 matrices of any shape (eval/ap_calculator.py:161,
+ * 193,250), one CTA per matrix: matrix b is nr[b] x nc[b] row-major at cost + c_off[b]; `work` is a
+ * scratch buffer of the same size and offsets (holds the transpose of tall matrices).
+ * col_of_row[r_off[b]+i] = column of row i or -1; matched_cost (optional, same indexing) = the cost
+ * of that pair (what the reference reads back as cost[row_ind, col_ind] at :163,195,251), so the
+ * matrices themselves never leave the device; status[b] = WF_LSAP_*.  WF_ETOOBIG when
+ * max(max_nr,max_nc) needs more than 200 KB of shared memory (~ 9 000). */
+int wf_lsap_f64(const double* cost, const int64_t* c_off, const int32_t* nr, const int32_t* nc,
+                const int64_t* r_off, int B, int max_nr, int max_nc, double* work,
+                int32_t* col_of_row, double* matched_cost, int32_t* status, wf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,9 @@ SIGNATURES = {
     "wf_edge_pair_bwd": [P, P, P, P, P, P, I, I, I, P, P, P, P, P],
     "wf_edge_out_fwd": [P, P, P, P, I, I, I, P, P],
     "wf_edge_out_bwd": [P, P, P, P, P, I, I, I, P, P, P, P],
+    "wf_hausdorff_lines": [P, P, P, P, P, I, I, P, I, P, P],
+    "wf_cdist_f64": [P, P, P, P, P, I, L, I, P, P],
+    "wf_lsap_f64": [P, P, P, P, P, I, I, I, P, P, P, P, P],
     "wf_loss_out_floats": [],
     "wf_loss_fwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, F, F, F, P, P],
     "wf_loss_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, F, F, P, P, P, P],
