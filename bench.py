@@ -17,6 +17,7 @@ One JSON line is printed by rank 0; see README / DESIGN.md for the keys.  The or
 the `cpu_baseline` leg and by `--impl reference`, as the thing being compared against -- never by the product path.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -65,14 +66,47 @@ def make_batch(rank, B):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (profiling recipe's clocks line)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (profiling recipe's clocks line).
+    In-process NVML polling (nvidia_ml_py) every 20 ms: NVML is initialised before the warm-up, so the driver-wide
+    initialisation an external `nvidia-smi` does at start-up (it touches every GPU of the box and showed up as 5-17 ms
+    outlier steps at 8 GPUs) cannot land inside the timed region.  Falls back to `nvidia-smi -lms` without NVML."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.rows, self.on, self.nvml, self.handle = index, None, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        flags = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+        while self.on:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((float(sm), float(self.max_sm), pw, [k for k, bit in flags if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        self.rows, self.on = [], True
+        if self.nvml is not None:
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -82,32 +116,30 @@ class ClockSampler:
             self.proc = None
 
     def _pump(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            f = [t.strip() for t in ln.split(",")]
+            try:
+                self.rows.append((float(f[0]), float(f[1]), float(f[2]),
+                                  [k for k, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+            except (ValueError, IndexError):
+                continue
 
     def stop(self):
+        self.on = False
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        rows = list(self.rows)
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted({r for row in rows for r in row[3]})
+        return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": max(r[1] for r in rows),
+                "power_w_max": max(r[2] for r in rows), "reasons": reasons, "samples": len(rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def peaks():
@@ -243,13 +275,24 @@ def main_gpu(args):
     step_ms = {False: [], True: []}
     copy_stream = torch.cuda.Stream(dev)
 
-    def h2d():
-        """This step's inputs from pinned host memory, on the copy stream (overlaps the previous step's compute)."""
+    # two preallocated device staging sets (double buffer): the per-step copy never touches the caching allocator
+    stage = [(torch.empty_like(x), {k: torch.empty_like(v) for k, v in tgt.items()}) for _ in range(2)]
+    stage_free = [None, None]                     # event: the step that last read this set has finished
+
+    def h2d(slot):
+        """This step's inputs from pinned host memory into staging set `slot`, on the copy stream (overlaps the previous
+        step's compute; waits until the step that last used the set is done)."""
+        xs, tg = stage[slot]
         with torch.cuda.stream(copy_stream):
-            xin = x_pin.to(dev, non_blocking=True)
-            tg = {k: v.to(dev, non_blocking=True) for k, v in tgt_pin.items()}
+            if stage_free[slot] is not None:
+                copy_stream.wait_event(stage_free[slot])
+            xs.copy_(x_pin, non_blocking=True)
+            for k, v in tgt_pin.items():
+                tg[k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event(); ev.record(copy_stream)
-        return xin, tg, ev
+            for t in tg.values():
+                ops.mark_ready(t, ev)             # as wf_b200.targets.DevicePrefetcher tags what it stages
+        return xs, tg, ev
 
     def timed(n, e2e):
         """n steps, each bracketed by CUDA events, L2 flushed between steps (outside the events).  e2e: every step issues the
@@ -263,13 +306,12 @@ def main_gpu(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:
-                cur = nxt if nxt is not None else h2d()
-                nxt = h2d() if i + 1 < n else None
+                cur = nxt if nxt is not None else h2d(i % 2)
+                nxt = h2d((i + 1) % 2) if i + 1 < n else None
                 xin, tg, ev = cur
                 torch.cuda.current_stream().wait_event(ev)
-                for t in (xin, *tg.values()):
-                    t.record_stream(torch.cuda.current_stream())
                 step(xin, tg, True)                                         # D2H: the loss scalar
+                stage_free[i % 2] = torch.cuda.Event(); stage_free[i % 2].record()
             else:
                 step(x, tgt, False)
             e1.record()
@@ -278,10 +320,13 @@ def main_gpu(args):
             step_ms[e2e].append(round(e0.elapsed_time(e1), 3))
         return total_ms
 
+    sampler = ClockSampler(local) if rank == 0 else None      # NVML initialised here, before the warm-up
     for _ in range(max(args.warmup, 3)):
         step(x, tgt, False)
     barrier()
-    sampler = ClockSampler(local)
+    gc.collect()
+    gc.freeze()                                   # the long-lived module/optimizer objects leave the collector's young
+    #                                               generations: no multi-ms collection pause lands on one rank mid-step
     if rank == 0:
         sampler.start()
     # ---- timed region 1: device-resident inputs, kernel-level GEMM timing on the launching stream
@@ -294,7 +339,7 @@ def main_gpu(args):
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: end to end through the public API with host buffers (two untimed steps first: the pinned
-    #      staging path allocates its device buffers on first use)
+    #      staging path is exercised once per buffer set first)
     barrier()
     timed(2, e2e=True)
     step_ms[True].clear()

@@ -28,6 +28,12 @@ class WireframeLoss(nn.Module):
         #   False      never read.
         self.check_status = "deferred"
         self._pending = None
+        # The matching needs the vertex head's outputs only, not the edge head's.  When the model tagged them with a
+        # ready-event (PointCloudToWireframe.forward) and the targets are known to be complete -- tagged the same way
+        # by wf_b200.targets, or the very tensors already used by the previous call, as in train.py's loop -- the
+        # assignment runs on a side stream beside the edge head instead of after it.  Otherwise: main stream.
+        self.overlap_matching = True
+        self._seen_targets = None
 
     @staticmethod
     def _raise_for(st):
@@ -48,6 +54,40 @@ class WireframeLoss(nn.Module):
         mode = self.check_status if sync is None else sync
         if mode == "deferred":
             self.check_pending()
+        waits = self._overlap_events(predictions, targets) if self.overlap_matching else None
+        if waits is None:
+            return self._launch_match(predictions, targets, mode)
+        main = torch.cuda.current_stream()
+        side = ops.side_stream(predictions['vertices'].device)
+        for ev in waits:
+            side.wait_event(ev)
+        with torch.cuda.stream(side):
+            col = self._launch_match(predictions, targets, mode)
+            done = torch.cuda.Event()
+            done.record(side)
+        main.wait_event(done)
+        col.record_stream(main)
+        return col
+
+    def _overlap_events(self, predictions, targets):
+        """Events the side stream must wait for, or None when the targets' completion cannot be established."""
+        ready = getattr(predictions['vertices'], '_wf_ready', None)
+        if ready is None:
+            return None
+        waits = [ready]
+        sig = []
+        for k in ('vertices', 'vertex_counts'):
+            t = targets[k]
+            ev = getattr(t, '_wf_ready', None)
+            if ev is not None:
+                waits.append(ev)
+            sig.append((t.data_ptr(), t._version, tuple(t.shape), ev is not None))
+        seen, self._seen_targets = self._seen_targets, sig
+        if all(s[3] for s in sig) or seen == sig:
+            return waits
+        return None
+
+    def _launch_match(self, predictions, targets, mode):
         col, status, _ = ops.loss_match(predictions['vertices'], predictions['existence_probabilities'],
                                         targets['vertices'], targets['vertex_counts'])
         if mode is True:

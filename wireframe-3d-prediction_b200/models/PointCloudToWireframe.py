@@ -39,6 +39,9 @@ class PointCloudToWireframe(nn.Module):
         global_features = self.encoder.fuse(max_m, avg_m)
         vo = self.vertex_predictor.forward_pooled(global_features, mean_u, max_u)
         verts, prob, dyn = vo['vertices'], vo['existence_probabilities'], vo['actual_vertex_counts']
+        # everything the loss's matching step reads is final here; the edge head below does not touch it, so the loss
+        # may start matching beside the edge head (losses/WireframeLoss.py, _match_device)
+        ops.mark_ready(verts)
         batch_size = verts.shape[0]
         if self.training and target_vertex_counts is not None:
             counts = self._host_counts(target_vertex_counts)

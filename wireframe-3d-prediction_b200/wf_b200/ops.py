@@ -56,6 +56,30 @@ def _s():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that is independent of what the main stream is running
+    (the loss matching runs there, beside the edge head)."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(idx)
+    return _SIDE_STREAMS[idx]
+
+
+def mark_ready(t: torch.Tensor, event=None) -> torch.Tensor:
+    """Tag a tensor with the CUDA event after which its contents are complete (recorded now on the current stream
+    unless given).  Consumers that want to read it from another stream wait on `t._wf_ready` instead of on the whole
+    main stream."""
+    if event is None:
+        event = torch.cuda.Event()
+        event.record()
+    t._wf_ready = event
+    return t
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:

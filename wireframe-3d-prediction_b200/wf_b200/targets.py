@@ -50,6 +50,10 @@ def prepare_targets(wf_vertices: Sequence[torch.Tensor], wf_edges: Sequence[torc
         call("wf_pack_targets", ops._p(dv), ops._p(doff[0]), ops._p(de), ops._p(doff[1]), B, V, max_e, E, ops._p(out["vertices"]),
              ops._p(out["vertex_existence"]), ops._p(out["vertex_counts"]), ops._p(out["edge_labels"]), ops._s())
     ops._count()
+    done = torch.cuda.Event()
+    done.record()
+    for t in out.values():
+        ops.mark_ready(t, done)          # lets WireframeLoss start its matching on a side stream (see _match_device)
     return out
 
 
@@ -81,6 +85,9 @@ class DevicePrefetcher:
                     dev_batch[k] = v
             ev = torch.cuda.Event()
             ev.record(self.stream)
+            for v in dev_batch.values():
+                if torch.is_tensor(v):
+                    ops.mark_ready(v, ev)
         self._next = (dev_batch, ev)
 
     def __iter__(self):
