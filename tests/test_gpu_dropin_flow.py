@@ -143,12 +143,13 @@ def test_train_py_then_evaluate_py_call_sequence(tmp_path):
             batch = {"predicted_vertices": pred_vertices[np.newaxis, :], "predicted_edges": pd_edges[np.newaxis, :],
                      "pred_edges_vertices": pev.reshape((1, -1, 2, 3)), "wf_vertices": gt_vertices[np.newaxis, :],
                      "wf_edges": gt_edges[np.newaxis, :], "wf_edges_vertices": gev.reshape((1, -1, 2, 3))}
-            ap_calculator.compute_metrics(batch)
-            # the batched helper builds the same dictionary
+            # the batched helper builds the same dictionary (compared first: compute_metrics snaps matched segments
+            # onto their labels inside the caller's array, eval/ap_calculator.py:233-234)
             from wf_b200.evalpost import make_ap_batch
             fastb = make_ap_batch(predictions, gts_v, gts_e)
             assert np.array_equal(fastb["predicted_edges"][i], pd_edges)
             assert np.array_equal(fastb["pred_edges_vertices"][i], pev) or len(pd_edges) == 0
+            ap_calculator.compute_metrics(batch)
     with contextlib.redirect_stdout(io.StringIO()) as text:
         ap_calculator.output_accuracy()
     assert "Corners Precision" in text.getvalue()

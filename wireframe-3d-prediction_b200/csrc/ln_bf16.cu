@@ -166,9 +166,13 @@ ln_relu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, co
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                    uint4* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum,
                    long long M) {
-    constexpr int C8 = NW * 32, C = C8 * 8;
+    constexpr int C8 = NW * 32, C = C8 * 8, NV = 2 * RG;    // NV row sums per group: (sum gh, sum gh*xhat) x RG rows
     extern __shared__ uint4 ring[];                       // [STAGES][2 (dh, z)][RG][C8]
-    __shared__ float red[2][NW][2 * RG];
+    // Row sums: every thread deposits its NV partials ([value][thread], conflict-free), warp w then reduces values
+    // w, w+NW, ... (NW consecutive partials per lane, one warp reduction each) -- 1/6 of the instructions of reducing all NV
+    // values in every warp and combining the warps' results in every thread.
+    __shared__ __align__(16) float partial[NV][C8];
+    __shared__ __align__(16) float rowsum[NV];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring)) + tid * 16;
     u64 gm[4], bt[4];
@@ -193,67 +197,94 @@ ln_relu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z, co
         cp_async_commit();
     };
 
+    // row statistics of a group (RG = 4 rows -> one aligned float4 each); fetched one group AHEAD into registers: read on
+    // demand they cost every group a full global-memory latency that nothing else in the loop covers
+    auto load_stats = [&](long long g, float4& m4, float4& r4) {
+        m4 = make_float4(0.f, 0.f, 0.f, 0.f); r4 = m4;
+        if (g < groups) {
+            const long long r0 = g * RG;
+            if (r0 + RG <= M) {
+                m4 = __ldg(reinterpret_cast<const float4*>(mean + r0)); r4 = __ldg(reinterpret_cast<const float4*>(rstd + r0));
+            } else {
+                float* pm = reinterpret_cast<float*>(&m4); float* pr = reinterpret_cast<float*>(&r4);
+                for (int r = 0; r < RG; ++r) if (r0 + r < M) { pm[r] = mean[r0 + r]; pr[r] = rstd[r0 + r]; }
+            }
+        }
+    };
+    static_assert(RG == 4, "statistics are fetched as one float4 per group");
+
     long long grp = blockIdx.x;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) issue(grp + (long long)s * gridDim.x, s);
-    int stage = 0, buf = 0;
-    for (; grp < groups; grp += gridDim.x, buf ^= 1) {
+    float4 mu_next, rs_next;
+    load_stats(grp, mu_next, rs_next);
+    int stage = 0;
+    for (; grp < groups; grp += gridDim.x) {
         issue(grp + (long long)(STAGES - 1) * gridDim.x, stage == 0 ? STAGES - 1 : stage - 1);
+        const float mu[RG] = {mu_next.x, mu_next.y, mu_next.z, mu_next.w};
+        const float rs[RG] = {rs_next.x, rs_next.y, rs_next.z, rs_next.w};
+        load_stats(grp + gridDim.x, mu_next, rs_next);
         cp_async_wait<STAGES - 1>();                                         // this thread's copies of `grp` have landed
         const long long r0 = grp * RG;
-        const uint4* sd = ring + ((stage * 2 + 0) * RG) * C8 + tid;
+        uint4* sd = ring + ((stage * 2 + 0) * RG) * C8 + tid;                // this thread's own 16 bytes of each row
         const uint4* sz = ring + ((stage * 2 + 1) * RG) * C8 + tid;
-        float part[2 * RG], mu[RG], rs[RG];
-#pragma unroll
-        for (int r = 0; r < RG; ++r) {
-            const bool ok = r0 + r < M;
-            mu[r] = ok ? mean[r0 + r] : 0.f; rs[r] = ok ? rstd[r0 + r] : 0.f;
-        }
 #pragma unroll
         for (int r = 0; r < RG; ++r) {
             const uint4 ud = sd[r * C8], uz = sz[r * C8];
             const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wz[4] = {uz.x, uz.y, uz.z, uz.w};
             const u64 rs2 = pk2(rs[r], rs[r]), nm2 = pk2(-mu[r] * rs[r], -mu[r] * rs[r]);
             u64 a = 0ull, b = 0ull;
+            uint32_t gw[4];                                                  // g = dh * [y > 0], still exact in bf16
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const u64 xh = fma2(bf2(wz[i]), rs2, nm2);
-                float y0, y1, d0, d1;
+                float y0, y1;
                 up2(fma2(xh, gm[i], bt[i]), y0, y1);
-                up2(bf2(wd[i]), d0, d1);
-                const u64 gh = mul2(pk2(y0 > 0.f ? d0 : 0.f, y1 > 0.f ? d1 : 0.f), gm[i]);
+                gw[i] = wd[i] & ((y0 > 0.f ? 0x0000FFFFu : 0u) | (y1 > 0.f ? 0xFFFF0000u : 0u));
+                const u64 gh = mul2(bf2(gw[i]), gm[i]);
                 a = add2(a, gh); b = fma2(gh, xh, b);
             }
+            sd[r * C8] = make_uint4(gw[0], gw[1], gw[2], gw[3]);             // the second pass reads g, not dh
             float lo, hi;
-            up2(a, lo, hi); part[2 * r] = lo + hi;
-            up2(b, lo, hi); part[2 * r + 1] = lo + hi;
+            up2(a, lo, hi); partial[2 * r][tid] = lo + hi;
+            up2(b, lo, hi); partial[2 * r + 1][tid] = lo + hi;
         }
+        __syncthreads();
+        for (int k = warp; k < NV; k += NW) {
+            float t = 0.f;
+            if (NW % 4 == 0) {
 #pragma unroll
-        for (int k = 0; k < 2 * RG; ++k) part[k] = warp_sum(part[k]);
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 2 * RG; ++k) red[buf][warp][k] = part[k];
+                for (int j = 0; j < NW / 4; ++j) {
+                    const float4 v = reinterpret_cast<const float4*>(&partial[k][lane * NW])[j];
+                    t += (v.x + v.y) + (v.z + v.w);
+                }
+            } else {
+                const float2 v = *reinterpret_cast<const float2*>(&partial[k][lane * NW]);
+                t = v.x + v.y;
+            }
+            t = warp_sum(t);
+            if (lane == 0) rowsum[k] = t;
         }
-        __syncthreads();                       // double-buffered: the next group's writes go to the other buffer
+        __syncthreads();
+        float cs[NV];
+#pragma unroll
+        for (int k = 0; k < NV / 4; ++k) {
+            const float4 v = reinterpret_cast<const float4*>(rowsum)[k];
+            cs[4 * k] = v.x; cs[4 * k + 1] = v.y; cs[4 * k + 2] = v.z; cs[4 * k + 3] = v.w;
+        }
 #pragma unroll
         for (int r = 0; r < RG; ++r) {
             if (r0 + r >= M) break;
-            float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) { c1 += red[buf][w][2 * r]; c2 += red[buf][w][2 * r + 1]; }
-            c1 *= (1.0f / C); c2 *= (1.0f / C);
-            const uint4 ud = sd[r * C8], uz = sz[r * C8];
-            const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wz[4] = {uz.x, uz.y, uz.z, uz.w};
+            const float c1 = cs[2 * r] * (1.0f / C), c2 = cs[2 * r + 1] * (1.0f / C);
+            const uint4 ug = sd[r * C8], uz = sz[r * C8];
+            const uint32_t wg[4] = {ug.x, ug.y, ug.z, ug.w}, wz[4] = {uz.x, uz.y, uz.z, uz.w};
             const u64 rs2 = pk2(rs[r], rs[r]), nm2 = pk2(-mu[r] * rs[r], -mu[r] * rs[r]);
             const u64 k1 = pk2(-c1 * rs[r], -c1 * rs[r]), k2 = pk2(-c2 * rs[r], -c2 * rs[r]);
             uint32_t o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const u64 xh = fma2(bf2(wz[i]), rs2, nm2);
-                float y0, y1, d0, d1;
-                up2(fma2(xh, gm[i], bt[i]), y0, y1);
-                up2(bf2(wd[i]), d0, d1);
-                const u64 g = pk2(y0 > 0.f ? d0 : 0.f, y1 > 0.f ? d1 : 0.f);
+                const u64 g = bf2(wg[i]);
                 // dz = rstd * (g*gamma - c1 - xhat*c2)
                 const u64 dzv = fma2(xh, k2, fma2(mul2(g, gm[i]), rs2, k1));
                 acc_g[i] = add2(acc_g[i], g); acc_gx[i] = fma2(g, xh, acc_gx[i]); acc_dz[i] = add2(acc_dz[i], dzv);

@@ -35,6 +35,11 @@ class PointCloudToWireframe(nn.Module):
 
     def forward(self, point_cloud, target_vertex_counts=None):
         ops._need_cuda(point_cloud)
+        use_targets = self.training and target_vertex_counts is not None
+        # Training: the counts are an input.  Read them to the host BEFORE anything is enqueued: a fresh counts tensor
+        # (a new batch every step) costs one device->host read, and doing it here blocks the host while the device is
+        # idle anyway instead of draining the queue between the vertex head and the edge head.
+        counts = self._host_counts(target_vertex_counts) if use_targets else None
         max_m, avg_m, max_u, mean_u, _, _, _ = self.encoder.pooled(point_cloud)
         global_features = self.encoder.fuse(max_m, avg_m)
         vo = self.vertex_predictor.forward_pooled(global_features, mean_u, max_u)
@@ -43,9 +48,7 @@ class PointCloudToWireframe(nn.Module):
         # may start matching beside the edge head (losses/WireframeLoss.py, _match_device)
         ops.mark_ready(verts)
         batch_size = verts.shape[0]
-        if self.training and target_vertex_counts is not None:
-            counts = self._host_counts(target_vertex_counts)
-        else:
+        if not use_targets:
             counts = [int(c) for c in dyn.tolist()]                 # the one sync of the inference path
         counts = [min(int(c), self.max_vertices) for c in counts]  # reference slices [:count] of V rows
         if any(c <= 1 for c in counts):
