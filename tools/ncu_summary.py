@@ -1,0 +1,37 @@
+"""Condense an `ncu --set full` report into the few per-launch columns the design cites (profiles/*.csv).
+Usage: python tools/ncu_summary.py report.ncu-rep out.csv [kernel-substring]   (runs `ncu -i ... --page raw --csv`)"""
+import csv
+import subprocess
+import sys
+
+COLS = ["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__bytes.sum.per_second", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+
+
+def main(rep, out, needle=""):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr, units, data = rows[start], rows[start + 1], rows[start + 2:]
+    keep = [c for c in COLS if c in hdr]
+    idx = [hdr.index(c) for c in keep]
+    kn = hdr.index("Kernel Name")
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(keep)
+        w.writerow([units[i] for i in idx])
+        for r in data:
+            if needle in r[kn]:
+                w.writerow([r[i] for i in idx])
+    print(f"{out}: {sum(needle in r[kn] for r in data)} launches")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
