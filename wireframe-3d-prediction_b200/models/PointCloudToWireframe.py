@@ -35,6 +35,7 @@ class PointCloudToWireframe(nn.Module):
 
     def forward(self, point_cloud, target_vertex_counts=None):
         ops._need_cuda(point_cloud)
+        ops.new_step()            # gradient accumulators of this step come from one zero-filled buffer (ops.zeros_f32)
         use_targets = self.training and target_vertex_counts is not None
         # Training: the counts are an input.  Read them to the host BEFORE anything is enqueued: a fresh counts tensor
         # (a new batch every step) costs one device->host read, and doing it here blocks the host while the device is

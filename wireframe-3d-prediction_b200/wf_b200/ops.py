@@ -79,6 +79,48 @@ def mark_ready(t: torch.Tensor, event=None) -> torch.Tensor:
     t._wf_ready = event
     return t
 
+# ---- zero-initialised fp32 buffers (accumulators of the atomically reduced gradients) --------------------------------
+# A training step asks for ~80 of them (weight-gradient accumulators of split-K products, LayerNorm gain/shift/bias sums, ...),
+# each a separate fill launch.  Between two `new_step()` marks the requests are served as 256-byte-aligned views of ONE
+# buffer zeroed by a single fill, sized by what the previous step asked for; a step that asks for more than that (or code that
+# never marks steps) falls back to individual torch.zeros.  A buffer is never zeroed twice: views handed out (they become
+# parameter .grad tensors) keep their storage alive, the next step simply gets a new buffer.
+class _ZeroArena:
+    __slots__ = ("buf", "off", "need", "gen")
+
+    def __init__(self):
+        self.buf, self.off, self.need, self.gen = None, 0, 0, -1
+
+
+_ZERO_ARENAS = {}
+_STEP_GEN = 0
+
+
+def new_step() -> None:
+    """Marks the start of a training/inference step (PointCloudToWireframe.forward calls it)."""
+    global _STEP_GEN
+    _STEP_GEN += 1
+
+
+def zeros_f32(*shape, device) -> torch.Tensor:
+    dev = torch.device(device)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    a = _ZERO_ARENAS.get(dev.index)
+    if a is None:
+        a = _ZERO_ARENAS[dev.index] = _ZeroArena()
+    if a.gen != _STEP_GEN:
+        a.buf = torch.zeros(a.need, device=dev, dtype=torch.float32) if (a.need and a.gen >= 0) else None
+        a.off, a.need, a.gen = 0, 0, _STEP_GEN
+    n_al = (n + 63) & ~63
+    a.need += n_al
+    if a.buf is not None and n > 0 and a.off + n <= a.buf.numel():
+        v = a.buf[a.off:a.off + n].view(*shape)
+        a.off += n_al
+        return v
+    return torch.zeros(*shape, device=dev, dtype=torch.float32)
+
 
 def _need_cuda(*ts):
     for t in ts:
@@ -151,7 +193,7 @@ def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0,
             split = 1
         accumulate = split > 1 or (out is not None and beta == 1.0)
         if out is None:
-            out = (torch.zeros if accumulate else torch.empty)(M, N, device=A.device, dtype=torch.float32)
+            out = zeros_f32(M, N, device=A.device) if accumulate else torch.empty(M, N, device=A.device, dtype=torch.float32)
         elif beta == 0.0 and accumulate:
             out.zero_()
         call("wf_gemm_tf32", _p(A), A.stride(0), int(not transA), _p(B), B.stride(0), int(transB), M, N, K, _p(bias),
@@ -169,7 +211,7 @@ def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0,
 
 def colsum(x: torch.Tensor) -> torch.Tensor:
     x2 = x.reshape(-1, x.shape[-1])
-    out = torch.zeros(x2.shape[1], device=x.device, dtype=torch.float32)
+    out = zeros_f32(x2.shape[1], device=x.device)
     dt = BF16 if x2.dtype == torch.bfloat16 else F32
     call("wf_colsum", _p(x2), dt, x2.shape[0], x2.shape[1], x2.stride(0), _p(out), _s())
     _count()
@@ -231,9 +273,9 @@ class LinearLNAct(torch.autograd.Function):
         else:
             dz = torch.empty_like(d2)
             if gamma is not None:
-                dgamma = torch.zeros(C, device=d2.device, dtype=torch.float32)
-                dbeta = torch.zeros(C, device=d2.device, dtype=torch.float32)
-            db = torch.zeros(C, device=d2.device, dtype=torch.float32) if has_b else None
+                dgamma = zeros_f32(C, device=d2.device)
+                dbeta = zeros_f32(C, device=d2.device)
+            db = zeros_f32(C, device=d2.device) if has_b else None
             call("wf_ln_act_bwd", _p(d2), F32, _p(z), F32, _p(gamma), _p(beta), _p(mean), _p(rstd), int(act),
                  _p(keep), float(keep_scale), _p(dz), F32, _p(dgamma), _p(dbeta), _p(db), M, C, _s())
             _count()
@@ -275,8 +317,8 @@ class LNAct(torch.autograd.Function):
         M, C = z2.shape
         d2 = _f32c(dout.reshape(M, C))
         dz = torch.empty_like(d2)
-        dgamma = torch.zeros(C, device=d2.device, dtype=torch.float32)
-        dbeta = torch.zeros(C, device=d2.device, dtype=torch.float32)
+        dgamma = zeros_f32(C, device=d2.device)
+        dbeta = zeros_f32(C, device=d2.device)
         call("wf_ln_act_bwd", _p(d2), F32, _p(z2), F32, _p(gamma), _p(beta), _p(mean), _p(rstd), int(act), _p(keep),
              float(keep_scale), _p(dz), F32, _p(dgamma), _p(dbeta), None, M, C, _s())
         _count()
@@ -565,7 +607,7 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         sms = _sm_count()
 
         def weight_grad(dzl, hin, Nn, K):
-            dW = torch.zeros(Nn, K, device=dev, dtype=torch.float32)
+            dW = zeros_f32(Nn, K, device=dev)
             tiles = ((Nn + 127) // 128) * ((K + 255) // 256)
             split = max(1, min((M + 63) // 64, (2 * sms + tiles - 1) // tiles))
             gemm_bf16(dzl, hin, M=Nn, N=K, K=M, kmajor=False, out=dW, accumulate=True, split_k=split)
@@ -574,7 +616,7 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         hbar = ctx.hbar
         if hbar is not None:
             # pools -> final Linear, analytically (wf_pool_fused_bwd): no dense (M,512) gradient, no dX/dW GEMM for layer 5
-            G = torch.zeros(2 * B, C5, device=dev, dtype=torch.float32)
+            G = zeros_f32(2 * B, C5, device=dev)
             if gs[3] is not None:
                 G[:B].copy_(gs[3])
             if gs[1] is not None:
@@ -591,7 +633,7 @@ class EncoderPointMLP_TC(torch.autograd.Function):
             grads["W5"], grads["b5"] = dW5, db5
         else:
             dz = torch.empty(M, C5, device=dev, dtype=torch.bfloat16)
-            db5 = torch.zeros(C5, device=dev, dtype=torch.float32)
+            db5 = zeros_f32(C5, device=dev)
             call("wf_pool_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(arg_m), _p(arg_u),
                  _p(mask), _p(valid), B, N, C5, _p(dz), BF16, _p(db5), _s())
             _count()
@@ -606,9 +648,9 @@ class EncoderPointMLP_TC(torch.autograd.Function):
         for li, (W, g, be) in zip((2, 1, 0), ((W4, g4, be4), (W3, g3, be3), (W2, g2, be2))):
             Nn, K = W.shape
             dzl = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
-            dg = torch.zeros(Nn, device=dev, dtype=torch.float32)
-            dbe = torch.zeros(Nn, device=dev, dtype=torch.float32)
-            db = torch.zeros(Nn, device=dev, dtype=torch.float32)
+            dg = zeros_f32(Nn, device=dev)
+            dbe = zeros_f32(Nn, device=dev)
+            db = zeros_f32(Nn, device=dev)
             call("wf_ln_relu_bf16_bwd", _p(dh), _p(zs[li]), _p(means[li]), _p(rstds[li]), _p(g), _p(be), _p(dzl), _p(dg),
                  _p(dbe), _p(db), M, Nn, _s())
             _count()
@@ -618,10 +660,10 @@ class EncoderPointMLP_TC(torch.autograd.Function):
             dh = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
             gemm_bf16(dzl, cast_bf16(W, transpose=True), M=M, N=K, K=Nn, out=dh)
         C1 = W1.shape[0]
-        dW1 = torch.zeros(C1, D, device=dev, dtype=torch.float32)
-        db1 = torch.zeros(C1, device=dev, dtype=torch.float32)
-        dg1 = torch.zeros(C1, device=dev, dtype=torch.float32)
-        dbe1 = torch.zeros(C1, device=dev, dtype=torch.float32)
+        dW1 = zeros_f32(C1, D, device=dev)
+        db1 = zeros_f32(C1, device=dev)
+        dg1 = zeros_f32(C1, device=dev)
+        dbe1 = zeros_f32(C1, device=dev)
         dx = torch.empty(M, D, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         W1c = _f32c(W1)
         call("wf_enc_l1_bwd", _p(x), _p(W1c), _p(b1), _p(g1), _p(be1), _p(dh), BF16, _p(dW1), _p(db1), _p(dg1),
@@ -715,7 +757,7 @@ class GatherPrefix(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_packed):
         B, V = ctx.shape
-        d = torch.zeros(B, V, 3, device=d_packed.device, dtype=torch.float32)
+        d = zeros_f32(B, V, 3, device=d_packed.device)
         dpk = _f32c(d_packed)
         call("wf_scatter_prefix_add", _p(dpk), B, V, _p(ctx.rg.v_off), ctx.rg.T, _p(d), _s())
         _count()
@@ -779,8 +821,8 @@ class EdgePairLayer(torch.autograd.Function):
         dz1 = _f32c(dz1)
         dP = torch.empty(rg.T, C, device=dz1.device, dtype=torch.float32)
         dQ = torch.empty(rg.T, C, device=dz1.device, dtype=torch.float32)
-        dv = torch.zeros(rg.T, 3, device=dz1.device, dtype=torch.float32)
-        dwd = torch.zeros(C, device=dz1.device, dtype=torch.float32)
+        dv = zeros_f32(rg.T, 3, device=dz1.device)
+        dwd = zeros_f32(C, device=dz1.device)
         call("wf_edge_pair_bwd", _p(dz1), _p(dist), _p(verts), _p(wd), _p(rg.v_off), _p(rg.e_off), rg.B, rg.T, C, _p(dP),
              _p(dQ), _p(dv), _p(dwd), _s())
         _count()
@@ -808,8 +850,8 @@ class EdgeOut(torch.autograd.Function):
         h, w, probs = ctx.saved_tensors
         rg = ctx.rg
         dh = torch.empty_like(h)
-        dw = torch.zeros_like(w)
-        db = torch.zeros(1, device=h.device, dtype=torch.float32)
+        dw = zeros_f32(*w.shape, device=w.device)
+        db = zeros_f32(1, device=h.device)
         d_probs = _f32c(d_probs)
         call("wf_edge_out_bwd", _p(d_probs), _p(probs), _p(h), _p(w), _p(rg.e_off), rg.B, w.shape[0], rg.max_e,
              _p(dh), _p(dw), _p(db), _s())
