@@ -291,7 +291,7 @@ __device__ __forceinline__ int solve_any(const Work& w, int nr, int nc, int lane
     return solve_warp(w, nr, nc, lane);
 }
 
-constexpr int WARPS_PER_CTA = 4;
+constexpr int WARPS_PER_CTA = 4;          // fewer when a problem's working set is large (launch_cfg); kernels read blockDim
 
 // Generic: raw float32 matrices from global memory.
 __global__ void lsap_batched_kernel(const float* __restrict__ cost, long long batch_stride, int ld,
@@ -299,7 +299,7 @@ __global__ void lsap_batched_kernel(const float* __restrict__ cost, long long ba
                                     int32_t* __restrict__ col_of_row, int32_t* __restrict__ status, size_t per_warp) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * WARPS_PER_CTA + warp;
+    const int b = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (b >= B) return;
     const int nr0 = nr_arr[b], nc0 = nc_arr[b];
     int32_t* out = col_of_row + (size_t)b * max_nr;
@@ -330,7 +330,7 @@ __global__ void loss_match_kernel(const float* __restrict__ pred_v, const float*
                                   float* __restrict__ cost_dump, size_t per_warp) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * WARPS_PER_CTA + warp;
+    const int b = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (b >= B) return;
     const long long cnt = counts[b];
     int32_t* out = col_of_row + (size_t)b * V;
@@ -426,9 +426,12 @@ __global__ void detr_cost_kernel(const float* __restrict__ logits, const float* 
     cost[((size_t)b * Q + i) * ld + j] = c;
 }
 
-static int launch_cfg(size_t per_warp, size_t* smem_out, const void* kernel) {
-    const size_t smem = per_warp * WARPS_PER_CTA;
-    if (smem > 227 * 1024) { set_error("LSAP problem too large for shared memory (%zu bytes per CTA)", smem); return WF_ETOOBIG; }
+static int launch_cfg(size_t per_warp, size_t* smem_out, int* warps_out, const void* kernel) {
+    int warps = WARPS_PER_CTA;
+    while (warps > 1 && per_warp * warps > 227 * 1024) warps >>= 1;       // large matrices: fewer samples per CTA
+    const size_t smem = per_warp * warps;
+    *warps_out = warps;
+    if (smem > 227 * 1024) { set_error("LSAP problem too large for shared memory (%zu bytes per matrix)", smem); return WF_ETOOBIG; }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WF_ECUDA; }
@@ -448,9 +451,10 @@ extern "C" int wf_loss_match(const float* pred_v, const float* pred_e, const flo
     WF_CHECK_ARG(Vt >= 0, "wf_loss_match: bad Vt");
     size_t smem;
     const size_t per_warp = work_bytes(V, V);
-    int rc = launch_cfg(per_warp, &smem, (const void*)loss_match_kernel);
+    int warps;
+    int rc = launch_cfg(per_warp, &smem, &warps, (const void*)loss_match_kernel);
     if (rc != WF_OK) return rc;
-    loss_match_kernel<<<cdiv(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, smem, as_stream(stream)>>>(
+    loss_match_kernel<<<cdiv(B, warps), warps * 32, smem, as_stream(stream)>>>(
         pred_v, pred_e, tgt_v, reinterpret_cast<const long long*>(counts), B, V, Vt, col_of_row, status, cost_dump, per_warp);
     WF_LAUNCH_CHECK();
     return WF_OK;
@@ -465,9 +469,10 @@ extern "C" int wf_lsap_batched(const float* cost, int64_t batch_stride, int ld, 
     // worst case carve for any (nr<=max_nr, nc<=max_nc) after transposition: rows<=cols
     const size_t per_warp = work_bytes(lo > 0 ? lo : 1, hi > 0 ? hi : 1);
     size_t smem;
-    int rc = launch_cfg(per_warp, &smem, (const void*)lsap_batched_kernel);
+    int warps;
+    int rc = launch_cfg(per_warp, &smem, &warps, (const void*)lsap_batched_kernel);
     if (rc != WF_OK) return rc;
-    lsap_batched_kernel<<<cdiv(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, smem, as_stream(stream)>>>(
+    lsap_batched_kernel<<<cdiv(B, warps), warps * 32, smem, as_stream(stream)>>>(
         cost, (long long)batch_stride, ld, nr, nc, B, max_nr, col_of_row, status, per_warp);
     WF_LAUNCH_CHECK();
     return WF_OK;
