@@ -28,17 +28,25 @@
 namespace wf {
 namespace tc {
 
+// packed fp32 pairs (FADD2 / FFMA2): the epilogue's bias add and row statistics
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void up2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // One k-block is 128 bytes of K per row for either element type: 64 bf16 or 32 tf32 (fp32 storage).  All shared-memory
 // byte sizes are therefore identical for both; only element counts differ.
 constexpr int BM = 128, BN = 256, STAGES = 4;
 constexpr int A_BYTES = BM * 128;             // 16 KB
 constexpr int B_BYTES = BN * 128;             // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 512;                                 // barriers + TMEM slot; keeps the staging boxes 512-byte aligned
 constexpr int EPI_WARPS = 8;                                 // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int STG_TILE = 32 * 32;                            // floats: one 32x32 fp32 staging tile per epilogue warp, XOR-swizzled
 constexpr int STG_BYTES = EPI_WARPS * STG_TILE * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;
+constexpr int BIAS_BYTES = EPI_WARPS * 32 * 4;                // per epilogue warp: the 32 bias values of the chunk in flight
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + BIAS_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA)");
@@ -54,6 +62,7 @@ struct Params {
     const float* bias;
     void* D;
     int ldd, out_dtype, accumulate;
+    int tma_store;               // bf16 output written by TMA stores through map_d (plain tiles: no accumulate / split / pool)
     long long split_stride;      // > 0: split s stores (not adds) its partial tile at D + s * split_stride (deterministic split-K)
     float* rowstats;
     // pool mode (final encoder Linear, models/PointNetEncoder.py:94,103-111 + models/VertexPredictor.py:87): instead of
@@ -127,7 +136,8 @@ struct Sched {
 //         are multicast so each CTA's producer and epilogue see their own barriers flip.  Six 32 KB stages.
 template <int ESZ, bool A_KM, bool B_KM, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_d, const Params p) {
     constexpr bool MC = MODE == 1, TWO = MODE == 2, CL = MODE != 0;
     constexpr int NST = TWO ? 6 : STAGES;         // pipeline stages
     constexpr int BB = TWO ? B_BYTES / 2 : B_BYTES;
@@ -288,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int q = warp & 3;                                  // TMEM lane quarter this warp may read
         const int half = (warp - 4) >> 2;                        // which half of the tile's column chunks this warp owns
         float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (warp - 4) * STG_TILE;
-        const bool bias_v4 = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+        float* bias_slot = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES) + (warp - 4) * 32;
         int acc = 0; uint32_t acc_phase = 0;
         Sched sched(p, m_units, w_first, w_step);
         int n_blk, mu, kb0, kb1;
@@ -306,45 +316,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 pool_b0 = (p.pool_row0 + row0) / p.pool_n;
                 pool_rb = (pool_b0 + 1) * p.pool_n - (p.pool_row0 + row0);   // rows >= pool_rb belong to the next cloud
             }
+            const bool add_bias = p.bias != nullptr && kb0 == 0;       // split-K: the first K range carries the bias
+            // Bias: lane j fetches the value of column j of the NEXT chunk one chunk ahead (one register), so the load's
+            // latency hides behind the accumulator wait / the previous chunk; it reaches all rows (= threads) through a
+            // 128-byte per-warp slot of shared memory read back as broadcast float4s.  Columns beyond N get 0.
+            const int c_first = half * (BN / 64), c_end = (half + 1) * (BN / 64);
+            float bias_next = 0.f;
+            if (add_bias) { const int col = n_blk * BN + c_first * 32 + lane; if (col < p.N) bias_next = __ldg(p.bias + col); }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const bool add_bias = p.bias != nullptr && kb0 == 0;       // split-K: the first K range carries the bias
             // deterministic split-K: every K range has its own fp32 slice of the workspace, summed in order afterwards
             void* const Dt = p.split_stride > 0 ? static_cast<void*>(static_cast<float*>(p.D) + (long long)(kb0 / p.kb_per_split) * p.split_stride)
                                                 : p.D;
-            float s1 = 0.f, s2 = 0.f;
+            u64 s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;   // row (sum, sum of squares): two packed partial chains each
+            float s1 = 0.f, s2 = 0.f;                              // column-tail chunks
 #pragma unroll 1
-            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+            for (int c = c_first; c < c_end; ++c) {
                 const int col0 = n_blk * BN + c * 32;
                 if (col0 >= p.N) break;                          // warp-uniform
+                if (add_bias) {
+                    __syncwarp();
+                    bias_slot[lane] = bias_next;
+                    bias_next = 0.f;
+                    if (c + 1 < c_end) { const int col = col0 + 32 + lane; if (col < p.N) bias_next = __ldg(p.bias + col); }
+                    __syncwarp();
+                }
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
                 const bool full = col0 + 32 <= p.N;
-                float4 bb[8];                                    // bias requested before waiting for the accumulators
-                if (add_bias && full && bias_v4) {
+                float4 bb[8];
+                if (add_bias) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                    for (int j = 0; j < 8; ++j) bb[j] = reinterpret_cast<const float4*>(bias_slot)[j];
                 }
                 ptx::tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if (add_bias) {
-                    if (full && bias_v4) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w;
+                    for (int j = 0; j < 8; ++j) {
+                        up2(add2(pk2(v[4 * j], v[4 * j + 1]), pk2(bb[j].x, bb[j].y)), v[4 * j], v[4 * j + 1]);
+                        up2(add2(pk2(v[4 * j + 2], v[4 * j + 3]), pk2(bb[j].z, bb[j].w)), v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+                if (p.rowstats != nullptr) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const u64 a = pk2(v[j], v[j + 1]), b = pk2(v[j + 2], v[j + 3]);
+                            s1a = add2(s1a, a); s2a = fma2(a, a, s2a);
+                            s1b = add2(s1b, b); s2b = fma2(b, b, s2b);
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                            if (col0 + j < p.N) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
                     }
-                }
-                if (p.rowstats != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full || col0 + j < p.N) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
                 }
                 if (p.pool_n > 0) {
                     // ---- stage, then lane = column: running max / first argmax over this warp's rows, per cloud
@@ -374,6 +402,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                     __syncwarp();
+                } else if (p.tma_store) {
+                    // ---- bf16 through TMA: the thread (= row) converts its 32 columns and writes them as one 64-byte row of a
+                    // 32 x 32 box in the SWIZZLE_64B layout (16-byte unit ^= address bits 7-8: conflict-free for row-wise
+                    // writes); one lane hands the box to the copy engine, which clips rows >= M and columns >= N.  Two boxes
+                    // per warp alternate, so the warp never waits for a store it has just issued -- no read-back of the
+                    // staged tile, no per-thread global stores.
+                    const int buf = (c - c_first) & 1;
+                    if (lane == 0) ptx::bulk_wait_read<1>();              // the box written two chunks ago has been read
+                    __syncwarp();
+                    const uint32_t box_off = (uint32_t)(STAGES * STAGE_BYTES + BAR_BYTES + (warp - 4) * (STG_TILE * 4) + buf * 2048);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * k], v[8 * k + 1]), t1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]), t3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        uint32_t off = box_off + lane * 64 + k * 16;
+                        off ^= ((off >> 7) & 3u) << 4;
+                        *reinterpret_cast<uint4*>(smem + off) = pk;
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&map_d, smem_base + box_off, col0, row0);
+                        ptx::bulk_commit();
+                    }
                 } else if (full && !p.accumulate) {
                     // ---- stage, then row-contiguous stores
 #pragma unroll
@@ -428,8 +483,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
-            if (p.rowstats != nullptr && row_ok)     // one slot per (N tile, row): summed in tile order by wf_stats_finalize
-                reinterpret_cast<float2*>(p.rowstats)[(size_t)(2 * n_blk + half) * p.M + row] = make_float2(s1, s2);
+            if (p.rowstats != nullptr && row_ok) {   // one slot per (N tile, row): summed in tile order by wf_stats_finalize
+                float a0, a1, b0, b1;
+                up2(add2(s1a, s1b), a0, a1); up2(add2(s2a, s2b), b0, b1);
+                reinterpret_cast<float2*>(p.rowstats)[(size_t)(2 * n_blk + half) * p.M + row] = make_float2((a0 + a1) + s1, (b0 + b1) + s2);
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -438,6 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.tma_store && lane == 0) ptx::bulk_wait<0>();       // this warp's stores are complete before the CTA may exit
     }
 
     ptx::tc_fence_before();
@@ -501,13 +560,28 @@ static int make_map(CUtensorMap* m, int esz, bool mn_major, const void* ptr, uin
     return WF_OK;
 }
 
+// bf16 output [outer rows, inner columns], boxes of 32 x 32 elements (64-byte rows) in the 64-byte swizzle
+static int make_store_map(CUtensorMap* m, void* ptr, uint64_t inner, uint64_t outer, uint64_t ld) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return WF_ECUDA; }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2ull};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (store map) failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
+                                       (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return WF_ECUDA; }
+    return WF_OK;
+}
+
 }  // namespace tc
 }  // namespace wf
 
 namespace wf { namespace tc {
 
 template <int ESZ, bool A_KM, bool B_KM, int MC>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const Params& p, int grid, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -520,15 +594,15 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = MC != 0 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    WF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<ESZ, A_KM, B_KM, MC>, ma, mb, p));
+    WF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<ESZ, A_KM, B_KM, MC>, ma, mb, md, p));
     return WF_OK;
 }
 
 template <int ESZ, bool A_KM, bool B_KM>
-static int launch_mc(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t s) {
-    if (mode == 2) return launch<ESZ, A_KM, B_KM, 2>(ma, mb, p, grid, s);
-    if (mode == 1) return launch<ESZ, A_KM, B_KM, 1>(ma, mb, p, grid, s);
-    return launch<ESZ, A_KM, B_KM, 0>(ma, mb, p, grid, s);
+static int launch_mc(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const Params& p, int grid, cudaStream_t s) {
+    if (mode == 2) return launch<ESZ, A_KM, B_KM, 2>(ma, mb, md, p, grid, s);
+    if (mode == 1) return launch<ESZ, A_KM, B_KM, 1>(ma, mb, md, p, grid, s);
+    return launch<ESZ, A_KM, B_KM, 0>(ma, mb, md, p, grid, s);
 }
 
 // WF_B200_GEMM_MODE: 2 (default) = 2-SM MMA, 1 = 1-SM MMA with multicast B, 0 = no clusters
@@ -609,20 +683,25 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     }
     p.pool_n = 0; p.pool_row0 = 0; p.pool_idx0 = 0; p.pool_mask = nullptr; p.pool_max_u = nullptr; p.pool_max_m = nullptr;
     if (pool != nullptr) { p.pool_n = pool->n; p.pool_row0 = pool->row0; p.pool_idx0 = pool->idx0; p.pool_mask = pool->mask; p.pool_max_u = pool->max_u; p.pool_max_m = pool->max_m; }
+    // bf16 tiles that are simply stored leave through TMA (WF_B200_GEMM_TMA_STORE=0 keeps the per-thread stores)
+    static const bool tma_store_env = [] { const char* e = getenv("WF_B200_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+    p.tma_store = (tma_store_env && out_dtype == WF_BF16 && !p.accumulate && pool == nullptr && p.split_stride == 0) ? 1 : 0;
+    CUtensorMap md = ma;                                         // placeholder when unused
+    if (p.tma_store && (rc = make_store_map(&md, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd)) != WF_OK) return rc;
     long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
                                 : (long long)m_units * p.tiles_n * p.split_k;
     const int workers = (int)(items < workers_max ? items : workers_max);
     const int grid = mc ? 2 * workers : workers;
     const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
     switch (key) {
-        case 3: rc = launch_mc<2, true, true>(mode, ma, mb, p, grid, stream); break;
-        case 2: rc = launch_mc<2, true, false>(mode, ma, mb, p, grid, stream); break;
-        case 1: rc = launch_mc<2, false, true>(mode, ma, mb, p, grid, stream); break;
-        case 0: rc = launch_mc<2, false, false>(mode, ma, mb, p, grid, stream); break;
-        case 7: rc = launch_mc<4, true, true>(mode, ma, mb, p, grid, stream); break;
-        case 6: rc = launch_mc<4, true, false>(mode, ma, mb, p, grid, stream); break;
-        case 5: rc = launch_mc<4, false, true>(mode, ma, mb, p, grid, stream); break;
-        default: rc = launch_mc<4, false, false>(mode, ma, mb, p, grid, stream); break;
+        case 3: rc = launch_mc<2, true, true>(mode, ma, mb, md, p, grid, stream); break;
+        case 2: rc = launch_mc<2, true, false>(mode, ma, mb, md, p, grid, stream); break;
+        case 1: rc = launch_mc<2, false, true>(mode, ma, mb, md, p, grid, stream); break;
+        case 0: rc = launch_mc<2, false, false>(mode, ma, mb, md, p, grid, stream); break;
+        case 7: rc = launch_mc<4, true, true>(mode, ma, mb, md, p, grid, stream); break;
+        case 6: rc = launch_mc<4, true, false>(mode, ma, mb, md, p, grid, stream); break;
+        case 5: rc = launch_mc<4, false, true>(mode, ma, mb, md, p, grid, stream); break;
+        default: rc = launch_mc<4, false, false>(mode, ma, mb, md, p, grid, stream); break;
     }
     if (rc != WF_OK || !det) return rc;
     const long long mn4 = (long long)M * N / 4;
