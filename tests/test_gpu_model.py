@@ -399,3 +399,47 @@ def test_unusual_shapes_vs_oracle(B, N, V, max_count):
             assert_close(g, sdr[name].grad, 3e-3, name)
     finally:
         ops.set_precision("bf16")
+
+
+@pytest.mark.parametrize("input_dim", [3, 7])
+def test_fewer_input_features_use_the_tensor_core_encoder(input_dim):
+    """datasets/building3d.py:103-111: use_color / use_intensity off -> 3, 4 or 7 features.  The bf16 tensor-core encoder
+    takes them zero-padded to 8; results equal the generic fp32 path of the same module within the bf16 tolerance and the
+    oracle within it; the first layer's weight gradient has the module's own shape."""
+    from oracle import wireframe_oracle as wo
+    from models.PointNetEncoder import PointNetEncoder
+    from wf_b200 import ops
+    seed, B, N = 21, 2, 640
+    torch.manual_seed(0)
+    enc = PointNetEncoder(input_dim=input_dim).cuda()
+    assert enc._tc_shape
+    x, _, _ = wo.make_inputs(seed, B, N, 8, norm_intensity=True)
+    x = x[:, :, :input_dim].contiguous().cuda()
+    g = [torch.randn(B, 512, device="cuda") for _ in range(4)]
+    outs, grads = {}, {}
+    for prec in ("fp32", "bf16"):
+        ops.set_precision(prec)
+        enc.zero_grad()
+        r = enc.pooled(x)
+        # upstream gradients on the two MEAN pools only: max-pool routing is discontinuous under bf16-sized perturbations
+        # (tests/test_gpu_tc.py::test_encoder_tc_vs_fp32_path covers that case by norm)
+        (r[1] * g[1] + r[3] * g[3]).sum().backward()
+        outs[prec] = [t.detach().clone() for t in r[:4]]
+        grads[prec] = {k: p.grad.detach().clone() for k, p in enc.named_parameters() if p.grad is not None}
+    ops.set_precision("bf16")
+    assert grads["bf16"]["mlp.0.weight"].shape == (512, input_dim)
+    for a, b in zip(outs["bf16"], outs["fp32"]):
+        assert_close(a, b, 5e-2, "pooled features bf16 vs fp32 path")
+    for k in ("mlp.0.weight", "mlp.4.weight", "mlp.16.weight"):
+        ga, gb = grads["bf16"][k].double(), grads["fp32"][k].double()
+        assert float((ga - gb).norm() / gb.norm()) < 8e-2, k
+    # fp32 path vs the oracle (state dict of the same weights)
+    sd = {f"encoder.{k}": v.detach().cpu() for k, v in enc.state_dict().items()}
+    pf = wo.encoder_point_features(sd, x.cpu())
+    ref_max = pf.max(dim=1).values
+    assert_close(outs["fp32"][2], ref_max, 2e-4, "unmasked max vs oracle")
+    # inference (chunked, no grad) takes the same route
+    with torch.no_grad():
+        ri = enc.pooled(x)
+    for a, b in zip(ri[:4], outs["bf16"]):
+        assert torch.equal(a, b) or rel_err(a, b) < 1e-6

@@ -28,7 +28,25 @@ class PointNetEncoder(nn.Module):
             nn.Linear(output_dim * 4, output_dim * 2), nn.LayerNorm(output_dim * 2), nn.ReLU(inplace=True),
             nn.Linear(output_dim * 2, output_dim))
         self._n_hidden = len(hidden_dims)
-        self._tc_shape = (input_dim == 8 and list(hidden_dims) == [512, 1024, 2048, 1024] and output_dim == 512)
+        # the tensor-core path is built for the shipped widths; fewer input features (the dataset's use_color / use_intensity
+        # switches give 3, 4 or 7, datasets/building3d.py:103-111) ride on it zero-padded to 8
+        self._tc_shape = (1 <= input_dim <= 8 and list(hidden_dims) == [512, 1024, 2048, 1024] and output_dim == 512)
+        self._input_dim = input_dim
+
+    def tc_inputs(self, x):
+        """(x, parameter list) as the tensor-core encoder kernels take them: 8 input features."""
+        p = []
+        for li in range(self._n_hidden):
+            lin, ln = self.mlp[4 * li], self.mlp[4 * li + 1]
+            p += [lin.weight, lin.bias, ln.weight, ln.bias]
+        last = self.mlp[4 * self._n_hidden]
+        p += [last.weight, last.bias]
+        if x.shape[2] < 8:
+            # zero features and zero weight columns leave every activation unchanged (the centred layer's factorisation
+            # drops the rank-deficient directions); the pad's autograd slices the weight gradient back
+            x = torch.nn.functional.pad(x, (0, 8 - x.shape[2]))
+            p[0] = torch.nn.functional.pad(p[0], (0, 8 - p[0].shape[1]))
+        return x, p
 
     # ---- per-point MLP + the four pooled reductions (reference :85-111 and VertexPredictor :86-87)
     def pooled(self, x, want_point_features=False):
@@ -37,12 +55,7 @@ class PointNetEncoder(nn.Module):
         if x.dim() != 3:
             raise ValueError("expected point cloud of shape (batch, num_points, input_dim)")
         if ops.get_precision() == "bf16" and self._tc_shape:
-            p = []
-            for li in range(self._n_hidden):
-                lin, ln = self.mlp[4 * li], self.mlp[4 * li + 1]
-                p += [lin.weight, lin.bias, ln.weight, ln.bias]
-            last = self.mlp[4 * self._n_hidden]
-            p += [last.weight, last.bias]
+            x, p = self.tc_inputs(x)
             if (not torch.is_grad_enabled() and not want_point_features and ops.FUSED_POOL
                     and x.shape[1] >= ops._FUSED_MIN_POINTS):
                 # inference: chunked over points, nothing saved (evaluate.py:71 runs under torch.no_grad())

@@ -67,12 +67,7 @@ def encode_point_sharded(encoder, x_local: torch.Tensor, rank: int, world: int, 
     argmax indices are global point indices.  One exchange: reduce_pool_shards (3 small all-reduces)."""
     from . import ops
     n = x_local.shape[1]
-    p = []
-    for li in range(encoder._n_hidden):
-        lin, ln = encoder.mlp[4 * li], encoder.mlp[4 * li + 1]
-        p += [lin.weight, lin.bias, ln.weight, ln.bias]
-    last = encoder.mlp[4 * encoder._n_hidden]
-    p += [last.weight, last.bias]
+    x_local, p = encoder.tc_inputs(x_local)
     with torch.no_grad():
         return ops.encoder_pooled_infer(x_local, p, chunk_rows=chunk_rows, index_offset=rank * n, points_total=world * n,
                                         reduce_fn=lambda a, b, c: reduce_pool_shards(a, b, c, group))
