@@ -302,7 +302,7 @@ ln_act_fwd_v4_kernel(const float* __restrict__ z, const float* __restrict__ gamm
 // backward: column partial sums (dgamma, dbeta, bias gradient) stay in 12*VPT registers over all rows a thread sees;
 // NT == 32: the CTA's 8 warps are combined through shared memory first, then one atomic per column per CTA.
 template <int NT, int VPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NT == 32 && VPT == 4) ? 2 : 1)     // 512-wide rows per warp: two CTAs per SM (<= 128 registers)
 ln_act_bwd_v4_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd, int act,
                      const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ dz, float* __restrict__ dgamma,

@@ -174,6 +174,30 @@ edge_pair_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Q, c
     if (nj <= 0) return;
     const long long e0 = e_off[b] + pair_id(i, i + 1, c);
     const float vx = verts[(size_t)t * 3], vy = verts[(size_t)t * 3 + 1], vz = verts[(size_t)t * 3 + 2];
+    const int C4 = C >> 2;
+    if ((C & 3) == 0 && C4 <= (int)blockDim.x && (blockDim.x % C4) == 0 &&
+        ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(wd) |
+          reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(z1)) & 15) == 0) {
+        // a thread keeps four channels of this vertex's P row, the distance weights and the bias in registers and walks the
+        // partner vertices: one float4 of Q in, one float4 of z1 out per pair (the distance is formed once per 4 channels)
+        const int c4 = threadIdx.x % C4, j0 = threadIdx.x / C4, jstep = blockDim.x / C4;
+        const float4 p4 = reinterpret_cast<const float4*>(P + (size_t)t * C)[c4];
+        const float4 w4 = reinterpret_cast<const float4*>(wd)[c4];
+        const float4 b4 = reinterpret_cast<const float4*>(bias)[c4];
+        for (int jj = j0; jj < nj; jj += jstep) {
+            const int tj = t + 1 + jj;
+            const float dx = vx - verts[(size_t)tj * 3], dy = vy - verts[(size_t)tj * 3 + 1], dz = vz - verts[(size_t)tj * 3 + 2];
+            const float dd = sqrtf(dx * dx + dy * dy + dz * dz);
+            if (c4 == 0) dist[e0 + jj] = dd;
+            const float4 q4 = reinterpret_cast<const float4*>(Q + (size_t)tj * C)[c4];
+            // same association as the scalar form: ((P + Q) + wd * d) + bias
+            float4 o;
+            o.x = p4.x + q4.x + w4.x * dd + b4.x; o.y = p4.y + q4.y + w4.y * dd + b4.y;
+            o.z = p4.z + q4.z + w4.z * dd + b4.z; o.w = p4.w + q4.w + w4.w * dd + b4.w;
+            reinterpret_cast<float4*>(z1 + (size_t)(e0 + jj) * C)[c4] = o;
+        }
+        return;
+    }
     for (long long idx = threadIdx.x; idx < (long long)nj * C; idx += blockDim.x) {
         const int jj = (int)(idx / C), ch = (int)(idx - (long long)jj * C);
         const int tj = t + 1 + jj;
