@@ -14,7 +14,7 @@ whole batch in two device phases through `wf_b200.evalpost` (fp64 kernels of lib
            assignment problems (1 launch).
 
 Integer results (tp/fp/fn counts, assignments) are identical to the reference's, distances bit-equal
-fp64 (tests/test_gpu_evalpost.py).  Kept on purpose: the wireframe edit distance is computed from the
+fp64 (tests/test_gpu_evalpost.py; the host logic alone, with scipy in place of the kernels: tests/test_ap_host_logic.py).  Kept on purpose: the wireframe edit distance is computed from the
 LABEL edges (:232-237), `average_wed` divides by the size of the last batch (:143,276), a sample whose
 predicted edges all miss the threshold raises numpy's zero-size-reduction ValueError (:227), matched
 predicted segments are overwritten in the caller's array (:233-234).  Not kept: the debug prints of
@@ -63,10 +63,23 @@ def remove_corners(corner_a, corner_b):
     return keep.view(corner_a.dtype).reshape(-1, corner_a.shape[1])
 
 
+def _running_sum(values):
+    """sum of a 1-D array in ITS dtype, left to right (what `acc = 0; for v in values: acc += v` gives)"""
+    return np.cumsum(values)[-1] if len(values) else 0
+
+
+def _edge_lengths(vertices, edges):
+    """np.linalg.norm(vertices[a] - vertices[b]) per edge, in the vertices' dtype (float32 from the loader)"""
+    d = vertices[edges[:, 0]] - vertices[edges[:, 1]]
+    return np.sqrt(np.einsum('ij,ij->i', d, d))
+
+
 def _edit_distance_from(dist, pd_vertices, pd_edges, gt_vertices, gt_edges, wed_v):
-    """graph_edit_distance (:39-84) given dist = cdist(pd_vertices, gt_vertices)."""
-    wed_e = 0
-    left = gt_edges.copy()
+    """graph_edit_distance (:39-84) given dist = cdist(pd_vertices, gt_vertices).  The reference walks the submitted
+    edges one by one (a numpy row comparison against every label edge each time); the outcome only depends on which
+    index pairs occur, so the walk is done on integer pair codes."""
+    left = gt_edges
+    wrong = np.zeros(0, dtype=gt_vertices.dtype)             # lengths of submitted edges that are not label edges
     if len(pd_vertices) > 0:
         wed_v += sum(np.min(dist, axis=1))
         snapped = pd_vertices.copy()
@@ -75,21 +88,19 @@ def _edit_distance_from(dist, pd_vertices, pd_edges, gt_vertices, gt_edges, wed_
         new_id = np.asarray(new_id).reshape(-1)
         edges = np.unique(np.where(pd_edges >= 0, new_id[pd_edges], pd_edges), axis=0)
         where = _first_index_of_rows(gt_vertices)
-        for a, b in edges:
-            ia = where[_key(merged[a], gt_vertices.dtype)]
-            ib = where[_key(merged[b], gt_vertices.dtype)]
-            pair = np.array(sorted([ia, ib]))
-            if (gt_edges == pair).all(axis=1).any():
-                left = left[np.any(left != pair, axis=1)]
-            else:
-                wed_e += np.linalg.norm(merged[a] - merged[b])
+        first = np.array([where[_key(row, gt_vertices.dtype)] for row in merged], dtype=np.int64)
+        pairs = np.sort(first[edges], axis=1)                            # (:66) sorted([e1_index[0], e2_index[0]])
+        span = int(max(len(gt_vertices), gt_edges.max(initial=0) + 1))
+        code = pairs[:, 0] * span + pairs[:, 1]
+        gt_code = gt_edges[:, 0].astype(np.int64) * span + gt_edges[:, 1].astype(np.int64)
+        present = np.isin(code, gt_code)
+        left = gt_edges[~np.isin(gt_code, code[present])]                # every label edge equal to a submitted pair goes
+        wrong = _edge_lengths(merged, edges[~present])
     else:
         wed_v = 0
-    for a, b in left:
-        wed_e += np.linalg.norm(gt_vertices[a] - gt_vertices[b])
-    whole = 0
-    for a, b in gt_edges:
-        whole += np.linalg.norm(gt_vertices[a] - gt_vertices[b])
+    # the reference adds the lengths one by one to an int 0: wrong submissions first, then the label edges left over
+    wed_e = _running_sum(np.concatenate((wrong, _edge_lengths(gt_vertices, left))))
+    whole = _running_sum(_edge_lengths(gt_vertices, gt_edges))
     return (wed_e + wed_v) / whole
 
 
@@ -136,8 +147,9 @@ class APCalculator(object):
             hit = matched <= thr
             pr_pts = np.unique(seg[b][pi[hit]].reshape(-1, 3), axis=0)
             gt_pts = np.unique(gt_seg[b][li[hit]].reshape(-1, 3), axis=0)
-            sub_v = np.unique(gt_seg[b].reshape(-1, 3), axis=0)
-            state[b] = dict(hit=hit, pi=pi, li=li, pr_pts=pr_pts, gt_pts=gt_pts, sub_v=sub_v,
+            sub_v, sub_idx = np.unique(gt_seg[b].reshape(-1, 3), axis=0, return_inverse=True)
+            sub_e = np.sort(np.asarray(sub_idx).reshape(-1, 2), axis=-1)     # = computer_edges(gt_seg[b], sub_v)
+            state[b] = dict(hit=hit, pi=pi, li=li, pr_pts=pr_pts, gt_pts=gt_pts, sub_v=sub_v, sub_e=sub_e,
                             free_pr=remove_corners(corners[b], pr_pts), free_gt=remove_corners(gt_corners[b], gt_pts))
 
         # ---- phase 2: free-corner matrices (+ assignment), used-corner offsets, edit-distance snapping
@@ -164,8 +176,7 @@ class APCalculator(object):
                 distances += np.sum(np.min(used_d, axis=1))         # zero matched edges: numpy raises here
                 for j, i in enumerate(s['pi'][s['hit']]):
                     seg[b][i] = gt_seg[b][s['li'][s['hit']][j]]
-                sub_e = computer_edges(gt_seg[b], s['sub_v'])
-                wed = _edit_distance_from(snap_d, s['sub_v'], sub_e.copy(), gt_corners[b].copy(),
+                wed = _edit_distance_from(snap_d, s['sub_v'], s['sub_e'].copy(), gt_corners[b].copy(),
                                           gt_edges[b].copy(), distances)
             else:
                 pi, li, matched = first[b]
