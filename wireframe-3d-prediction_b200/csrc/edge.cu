@@ -41,6 +41,32 @@ __global__ void scatter_prefix_add_kernel(const float* __restrict__ d_packed, in
 // ------------------------------------------------------------------------------------------
 constexpr int HD_PAD = 1;
 
+// 4 x 4 register tile of a product of two shared-memory matrices given by strides:
+//   acc[u][v] = sum_{k < K} A[(i0 + u) * sai + k * sak] * B[k * sbk + (j0 + v) * sbj],   k ascending (one fmaf chain per output,
+// the same order as a scalar loop).  8 shared loads per 16 FMAs instead of 2 per FMA.  Rows/columns beyond the matrices'
+// logical extent are read (the arrays are padded to multiples of 4 rows) and their results discarded by the caller.
+__device__ __forceinline__ void smem_mm_4x4(const float* __restrict__ A, int sai, int sak, const float* __restrict__ B, int sbk,
+                                            int sbj, int K, int i0, int j0, float (&acc)[4][4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    const float* a0 = A + i0 * sai;
+    const float* b0 = B + j0 * sbj;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = a0[u * sai + k * sak];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) b[v] = b0[k * sbk + v * sbj];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+    }
+}
+
 template <int HD>
 __global__ void __launch_bounds__(256)
 attn_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ v_off, const long long* __restrict__ p_off,
@@ -50,8 +76,9 @@ attn_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ v_off, co
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int t0 = v_off[b], c = v_off[b + 1] - t0;
     if (c <= 0) return;
-    const int E = heads * HD, LD = HD + HD_PAD, LS = c + 1;
-    float* Q = sm; float* K = Q + c * LD; float* Vv = K + c * LD; float* S = Vv + c * LD;
+    const int cp = (c + 3) & ~3;                       // rows padded for the 4 x 4 tiles
+    const int E = heads * HD, LD = HD + HD_PAD, LS = cp + 1;
+    float* Q = sm; float* K = Q + cp * LD; float* Vv = K + cp * LD; float* S = Vv + cp * LD;
     const float scale = rsqrtf((float)HD);
     for (int idx = threadIdx.x; idx < c * HD; idx += blockDim.x) {
         const int i = idx / HD, d = idx - i * HD;
@@ -59,12 +86,15 @@ attn_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ v_off, co
         Q[i * LD + d] = row[0] * scale; K[i * LD + d] = row[E]; Vv[i * LD + d] = row[2 * E];
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
-        const int i = idx / c, j = idx - i * c;
-        float a = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < HD; ++d) a = fmaf(Q[i * LD + d], K[j * LD + d], a);
-        S[i * LS + j] = a;
+    const int tc = cp >> 2;
+    for (int tile = threadIdx.x; tile < tc * tc; tile += blockDim.x) {              // S = Qs K^T
+        const int i0 = (tile / tc) * 4, j0 = (tile % tc) * 4;
+        float acc[4][4];
+        smem_mm_4x4(Q, LD, 1, K, 1, LD, HD, i0, j0, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) S[(i0 + u) * LS + j0 + v] = acc[u][v];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,11 +114,16 @@ attn_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ v_off, co
         }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < c * HD; idx += blockDim.x) {
-        const int i = idx / HD, d = idx - i * HD;
-        float a = 0.f;
-        for (int j = 0; j < c; ++j) a = fmaf(S[i * LS + j], Vv[j * LD + d], a);
-        out[(size_t)(t0 + i) * E + h * HD + d] = a;
+    constexpr int TD = HD / 4;
+    for (int tile = threadIdx.x; tile < tc * TD; tile += blockDim.x) {              // out = P V
+        const int i0 = (tile / TD) * 4, d0 = (tile % TD) * 4;
+        float acc[4][4];
+        smem_mm_4x4(S, LS, 1, Vv, LD, 1, c, i0, d0, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u >= c) break;
+            *reinterpret_cast<float4*>(out + (size_t)(t0 + i0 + u) * E + h * HD + d0) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        }
     }
 }
 
@@ -101,10 +136,11 @@ attn_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ qkv, 
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int t0 = v_off[b], c = v_off[b + 1] - t0;
     if (c <= 0) return;
-    const int E = heads * HD, LD = HD + HD_PAD, LS = c + 1;
-    float* Q = sm; float* K = Q + c * LD; float* Vv = K + c * LD; float* dO = Vv + c * LD;
-    float* P = dO + c * LD;         // softmax probabilities (pre-dropout)
-    float* G = P + c * LS;          // dropped probabilities first, then dS
+    const int cp = (c + 3) & ~3;
+    const int E = heads * HD, LD = HD + HD_PAD, LS = cp + 1;
+    float* Q = sm; float* K = Q + cp * LD; float* Vv = K + cp * LD; float* dO = Vv + cp * LD;
+    float* P = dO + cp * LD;        // softmax probabilities (pre-dropout)
+    float* G = P + cp * LS;         // dropped probabilities first, then dS
     const float scale = rsqrtf((float)HD);
     const long long pbase = p_off[b] + (long long)h * c * c;
     for (int idx = threadIdx.x; idx < c * HD; idx += blockDim.x) {
@@ -120,22 +156,34 @@ attn_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ qkv, 
         G[i * LS + j] = keep ? (keep[pbase + idx] ? pv * keep_scale : 0.f) : pv;
     }
     __syncthreads();
+    const int tc = cp >> 2;
+    constexpr int TD = HD / 4;
     // dV[j][d] = sum_i Pd[i][j] dO[i][d]
-    for (int idx = threadIdx.x; idx < c * HD; idx += blockDim.x) {
-        const int j = idx / HD, d = idx - j * HD;
-        float a = 0.f;
-        for (int i = 0; i < c; ++i) a = fmaf(G[i * LS + j], dO[i * LD + d], a);
-        d_qkv[(size_t)(t0 + j) * 3 * E + 2 * E + h * HD + d] = a;
+    for (int tile = threadIdx.x; tile < tc * TD; tile += blockDim.x) {
+        const int j0 = (tile / TD) * 4, d0 = (tile % TD) * 4;
+        float acc[4][4];
+        smem_mm_4x4(G, 1, LS, dO, LD, 1, c, j0, d0, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j0 + u >= c) break;
+            *reinterpret_cast<float4*>(d_qkv + (size_t)(t0 + j0 + u) * 3 * E + 2 * E + h * HD + d0) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        }
     }
     __syncthreads();
     // dP[i][j] = keep * scale * sum_d dO[i][d] V[j][d]   (overwrites G)
-    for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
-        const int i = idx / c, j = idx - i * c;
-        float a = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < HD; ++d) a = fmaf(dO[i * LD + d], Vv[j * LD + d], a);
-        if (keep) a = keep[pbase + idx] ? a * keep_scale : 0.f;
-        G[i * LS + j] = a;
+    for (int tile = threadIdx.x; tile < tc * tc; tile += blockDim.x) {
+        const int i0 = (tile / tc) * 4, j0 = (tile % tc) * 4;
+        float acc[4][4];
+        smem_mm_4x4(dO, LD, 1, Vv, 1, LD, HD, i0, j0, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int i = i0 + u, j = j0 + v;
+                float a = acc[u][v];
+                if (keep && i < c && j < c) a = keep[pbase + (long long)i * c + j] ? a * keep_scale : 0.f;
+                G[i * LS + j] = a;
+            }
     }
     __syncthreads();
     // dS = P * (dP - rowsum(dP * P))
@@ -148,15 +196,22 @@ attn_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ qkv, 
     }
     __syncthreads();
     // dQ[i][d] = scale * sum_j dS[i][j] K[j][d];  dK[j][d] = sum_i dS[i][j] Qs[i][d]
-    for (int idx = threadIdx.x; idx < c * HD; idx += blockDim.x) {
-        const int i = idx / HD, d = idx - i * HD;
-        float a = 0.f, bk = 0.f;
-        for (int j = 0; j < c; ++j) {
-            a = fmaf(G[i * LS + j], K[j * LD + d], a);
-            bk = fmaf(G[j * LS + i], Q[j * LD + d], bk);
+    for (int tile = threadIdx.x; tile < tc * TD; tile += blockDim.x) {
+        const int i0 = (tile / TD) * 4, d0 = (tile % TD) * 4;
+        float acc[4][4];
+        smem_mm_4x4(G, LS, 1, K, LD, 1, c, i0, d0, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u >= c) break;
+            *reinterpret_cast<float4*>(d_qkv + (size_t)(t0 + i0 + u) * 3 * E + h * HD + d0) =
+                make_float4(acc[u][0] * scale, acc[u][1] * scale, acc[u][2] * scale, acc[u][3] * scale);
         }
-        float* row = d_qkv + (size_t)(t0 + i) * 3 * E + h * HD + d;
-        row[0] = a * scale; row[E] = bk;
+        smem_mm_4x4(G, 1, LS, Q, LD, 1, c, i0, d0, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u >= c) break;
+            *reinterpret_cast<float4*>(d_qkv + (size_t)(t0 + i0 + u) * 3 * E + E + h * HD + d0) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        }
     }
 }
 
@@ -337,8 +392,9 @@ extern "C" int wf_scatter_prefix_add(const float* d_packed, int B, int V, const 
 }
 
 static int attn_smem(int max_c, int hd, bool bwd, size_t* out) {
-    const size_t ld = hd + wf::edge::HD_PAD, ls = max_c + 1;
-    size_t fl = (bwd ? 4 : 3) * (size_t)max_c * ld + (bwd ? 2 : 1) * (size_t)max_c * ls;
+    const size_t cp = ((size_t)max_c + 3) & ~(size_t)3;          // rows padded for the kernels' 4 x 4 register tiles
+    const size_t ld = hd + wf::edge::HD_PAD, ls = cp + 1;
+    size_t fl = (bwd ? 4 : 3) * cp * ld + (bwd ? 2 : 1) * cp * ls;
     *out = fl * sizeof(float);
     if (*out > 227 * 1024) { wf::set_error("attention: %d vertices per sample exceed shared memory (%zu B)", max_c, *out); return WF_ETOOBIG; }
     return WF_OK;
