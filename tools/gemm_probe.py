@@ -51,6 +51,18 @@ def main():
         t = timeit(lambda: ops.gemm_bf16(dZ, A, M=N, N=K, K=M, kmajor=False, out=dW, accumulate=True, split_k=split))
         tt = timeit(lambda: torch.matmul(dZ.t(), A))
         print(f"dW   M={N:5d} N={K:5d} split={split}: wf {t:8.3f} ms {fl / t / 1e9:8.1f} TF/s | cublas {tt:8.3f} ms {fl / tt / 1e9:8.1f} TF/s")
+    # the pooling launch: final Linear 1024 -> 512 whose epilogue max-pools per cloud instead of storing
+    K, N, clouds = 1024, 512, 64
+    A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    mask = torch.ones(M, device=dev, dtype=torch.uint8)
+    packed = torch.zeros(2, clouds, N, device=dev, dtype=torch.int64)
+    t = timeit(lambda: ops.gemm_bf16_pool(A, W, M=M, N=N, K=K, bias=bias, points_per_cloud=M // clouds, row_offset=0, mask=mask, packed=packed))
+    mask[::7] = 0
+    t2 = timeit(lambda: ops.gemm_bf16_pool(A, W, M=M, N=N, K=K, bias=bias, points_per_cloud=M // clouds, row_offset=0, mask=mask, packed=packed))
+    fl = 2.0 * M * N * K
+    print(f"pool K={K:5d} N={N:5d}: wf {t:8.3f} ms {fl / t / 1e9:8.1f} TF/s (all points valid) | {t2:8.3f} ms {fl / t2 / 1e9:8.1f} TF/s (1/7 masked out)")
 
 
 if __name__ == "__main__":
