@@ -67,9 +67,11 @@ def make_batch(rank, B):
 
 class ClockSampler:
     """SM clock, power and throttle reasons sampled DURING the timed region (profiling recipe's clocks line).
-    In-process NVML polling (nvidia_ml_py) every 20 ms: NVML is initialised before the warm-up, so the driver-wide
-    initialisation an external `nvidia-smi` does at start-up (it touches every GPU of the box and showed up as 5-17 ms
-    outlier steps at 8 GPUs) cannot land inside the timed region.  Falls back to `nvidia-smi -lms` without NVML."""
+    NVML (nvidia_ml_py) is initialised before the warm-up and polled ONCE PER STEP from the main thread, right after the
+    step's launches have been enqueued and before the host waits for them: the device is in the middle of the step, and a
+    slow NVML call cannot delay a launch or another rank (a polling thread, and before it an external `nvidia-smi -lms`,
+    showed up as 10-100 ms outlier steps at 2-8 GPUs: NVML takes driver locks the launch path needs).  Step times come
+    from CUDA events, so host time spent here is not in them.  Falls back to `nvidia-smi -lms 100` without NVML."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -83,33 +85,33 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
             self.nvml = pynvml
+            self.flags = (("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap))
         except Exception:
             self.nvml = None
 
-    def _poll(self):
+    def poll_once(self):
+        """One sample; called by the timed loop while the device executes the step it has just been handed."""
+        if not self.on or self.nvml is None:
+            return
         n = self.nvml
-        flags = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
-                 ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
-                 ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
-        while self.on:
-            try:
-                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                self.rows.append((float(sm), float(self.max_sm), pw, [k for k, bit in flags if mask & bit]))
-            except Exception:
-                pass
-            time.sleep(0.02)
+        try:
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            self.rows.append((float(sm), float(self.max_sm), pw, [k for k, bit in self.flags if mask & bit]))
+        except Exception:
+            pass
 
     def start(self):
         self.rows, self.on = [], True
         if self.nvml is not None:
-            threading.Thread(target=self._poll, daemon=True).start()
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -139,7 +141,7 @@ class ClockSampler:
         reasons = sorted({r for row in rows for r in row[3]})
         return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": max(r[1] for r in rows),
                 "power_w_max": max(r[2] for r in rows), "reasons": reasons, "samples": len(rows),
-                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+                "source": "nvml, one sample per step while the step executes" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 def peaks():
@@ -315,21 +317,33 @@ def main_gpu(args):
             else:
                 step(x, tgt, False)
             e1.record()
+            if sampler is not None:
+                sampler.poll_once()                                         # the device is still executing this step
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)
             step_ms[e2e].append(round(e0.elapsed_time(e1), 3))
         return total_ms
 
-    sampler = ClockSampler(local) if rank == 0 else None      # NVML initialised here, before the warm-up
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local) if (rank == 0 and os.environ.get("WF_BENCH_NO_CLOCKS") != "1") else None   # NVML initialised before the warm-up
+    # Warm-up.  With more than one rank the first ~15 steps after start-up carry isolated 10-100 ms stalls on one rank
+    # (seen at 2, 4 and 8 GPUs with and without clock sampling or per-launch events, never later: diagnosis in DESIGN.md section 4),
+    # so multi-GPU runs settle for 20 further untimed steps; the JSON line reports the warm-up actually done.
+    n_warm = max(args.warmup, 3) + (20 if world > 1 else 0)
+    for _ in range(n_warm):
         step(x, tgt, False)
     barrier()
     gc.collect()
     gc.freeze()                                   # the long-lived module/optimizer objects leave the collector's young
     #                                               generations: no multi-ms collection pause lands on one rank mid-step
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     # ---- timed region 1: device-resident inputs, kernel-level GEMM timing on the launching stream
+    if os.environ.get("WF_BENCH_DIAG") == "1":          # diagnosis: the same region without the per-GEMM events, twice
+        for k in range(2):
+            barrier(); timed(args.steps, e2e=False); barrier()
+            if rank == 0:
+                print(f"diag region {k} (no GEMM events):", step_ms[False], file=sys.stderr, flush=True)
+            step_ms[False].clear()
     ops.GEMM_PROFILE = []
     l0 = ops.LAUNCHES
     barrier()
@@ -337,7 +351,7 @@ def main_gpu(args):
     barrier()
     launches = ops.LAUNCHES - l0
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     # ---- timed region 2: end to end through the public API with host buffers (two untimed steps first: the pinned
     #      staging path is exercised once per buffer set first)
     barrier()
@@ -359,7 +373,7 @@ def main_gpu(args):
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": samples / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world), "parallelism": f"dp{world}",
                        "l2": "256 MB buffer written between timed steps (outside the events); per-step working set ~11 GB",
