@@ -17,14 +17,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def fake_loader_batch(seed, B=3, N=2560):
+def fake_loader_batch(seed, B=3, N=2560, counts=(6, 9, 12)):
     """What collate_batch (datasets/building3d.py:171-190) hands to train.py: points (B,N,8) float32, ragged float32
     vertex and edge lists."""
     rng = np.random.default_rng(seed)
     xyz = rng.uniform(-1, 1, (B, N, 3))
     xyz /= np.linalg.norm(xyz, axis=2).max(axis=1)[:, None, None]
     pts = np.concatenate((xyz, rng.integers(0, 256, (B, N, 4)) / 256.0, rng.uniform(2e4, 6e4, (B, N, 1)) / 65536.0), axis=2)
-    counts = [6, 9, 12][:B]
+    counts = list(counts)[:B]
     verts = [torch.tensor(rng.uniform(-0.6, 0.6, (c, 3)).astype(np.float32)) for c in counts]
     edges = []
     for c in counts:
@@ -120,39 +120,49 @@ def test_train_py_then_evaluate_py_call_sequence(tmp_path):
     model2.load_state_dict(state_dict, strict=False)
     model2.eval()
     ap_calculator = APCalculator(distance_thresh=1)
-    test_batch = fake_loader_batch(0, B=1)                                            # per-sample probability rows need
-    with torch.no_grad():                                                             # equal lengths (evaluate.py:80-81)
-        pcs, gts_v, gts_e = test_batch["point_clouds"], test_batch["wf_vertices"], test_batch["wf_edges"]
-        vertex_counts = torch.tensor([len(v) for v in gts_v], dtype=torch.long).to(device)
-        predictions = model2(pcs.to(device), vertex_counts)
-        for i in range(len(gts_v)):
-            pred_vertices = predictions["vertices"][i].cpu().numpy()
-            edge_indices = predictions["edge_indices"][i]
-            edge_probs = predictions["edge_probs"][i].cpu().numpy()
-            mask = edge_probs > 0.5
-            pd_edges = np.array(edge_indices)[mask]
-            gt_vertices = gts_v[i].numpy()
-            gt_edges = gts_e[i].numpy().astype(np.int64)
-            if len(pd_edges) > 0:
-                pev = np.stack((pred_vertices[pd_edges[:, 0]], pred_vertices[pd_edges[:, 1]]), axis=1)
-                pev = pev[np.arange(pev.shape[0])[:, np.newaxis], np.flip(np.argsort(pev[:, :, -1]), axis=1)]
-            else:
-                pev = np.empty((0, 2, 3))
-            gev = np.stack((gt_vertices[gt_edges[:, 0]], gt_vertices[gt_edges[:, 1]]), axis=1)
-            gev = gev[np.arange(gev.shape[0])[:, np.newaxis], np.flip(np.argsort(gev[:, :, -1]), axis=1)]
-            batch = {"predicted_vertices": pred_vertices[np.newaxis, :], "predicted_edges": pd_edges[np.newaxis, :],
-                     "pred_edges_vertices": pev.reshape((1, -1, 2, 3)), "wf_vertices": gt_vertices[np.newaxis, :],
-                     "wf_edges": gt_edges[np.newaxis, :], "wf_edges_vertices": gev.reshape((1, -1, 2, 3))}
-            # the batched helper builds the same dictionary (compared first: compute_metrics snaps matched segments
-            # onto their labels inside the caller's array, eval/ap_calculator.py:233-234)
-            from wf_b200.evalpost import make_ap_batch
-            fastb = make_ap_batch(predictions, gts_v, gts_e)
-            assert np.array_equal(fastb["predicted_edges"][i], pd_edges)
-            assert np.array_equal(fastb["pred_edges_vertices"][i], pev) or len(pd_edges) == 0
-            ap_calculator.compute_metrics(batch)
+    for k in range(batch_size):                 # one building per batch: the per-sample probability rows of evaluate.py:80-81
+        test_batch = {"point_clouds": point_clouds[k:k + 1], "wf_vertices": [wf_vertices[k]], "wf_edges": [wf_edges[k]]}
+        with torch.no_grad():
+            pcs, gts_v, gts_e = test_batch["point_clouds"], test_batch["wf_vertices"], test_batch["wf_edges"]
+            vertex_counts = torch.tensor([len(v) for v in gts_v], dtype=torch.long).to(device)
+            predictions = model2(pcs.to(device), vertex_counts)
+            for i in range(len(gts_v)):
+                pred_vertices = predictions["vertices"][i].cpu().numpy()
+                edge_indices = predictions["edge_indices"][i]
+                edge_probs = predictions["edge_probs"][i].cpu().numpy()
+                mask = edge_probs > 0.5
+                pd_edges = np.array(edge_indices)[mask]
+                gt_vertices = gts_v[i].numpy()
+                gt_edges = gts_e[i].numpy().astype(np.int64)
+                if len(pd_edges) > 0:
+                    pev = np.stack((pred_vertices[pd_edges[:, 0]], pred_vertices[pd_edges[:, 1]]), axis=1)
+                    pev = pev[np.arange(pev.shape[0])[:, np.newaxis], np.flip(np.argsort(pev[:, :, -1]), axis=1)]
+                else:
+                    pev = np.empty((0, 2, 3))
+                gev = np.stack((gt_vertices[gt_edges[:, 0]], gt_vertices[gt_edges[:, 1]]), axis=1)
+                gev = gev[np.arange(gev.shape[0])[:, np.newaxis], np.flip(np.argsort(gev[:, :, -1]), axis=1)]
+                batch = {"predicted_vertices": pred_vertices[np.newaxis, :], "predicted_edges": pd_edges[np.newaxis, :],
+                         "pred_edges_vertices": pev.reshape((1, -1, 2, 3)), "wf_vertices": gt_vertices[np.newaxis, :],
+                         "wf_edges": gt_edges[np.newaxis, :], "wf_edges_vertices": gev.reshape((1, -1, 2, 3))}
+                # the batched helper builds the same dictionary (compared first: compute_metrics snaps matched segments
+                # onto their labels inside the caller's array, eval/ap_calculator.py:233-234)
+                from wf_b200.evalpost import make_ap_batch
+                fastb = make_ap_batch(predictions, gts_v, gts_e)
+                assert np.array_equal(fastb["predicted_edges"][i], pd_edges)
+                assert np.array_equal(fastb["pred_edges_vertices"][i], pev) or len(pd_edges) == 0
+                # ... and the oracle's restatement of the reference calculator, on the same arrays, must agree with the device path
+                from oracle import ap_oracle as ao
+                want = ao.sample_metrics(pred_vertices.copy(), pd_edges.copy(), pev.copy(), gt_vertices.copy(), gt_edges.copy(),
+                                         gev.copy(), 1)
+                before = dict(ap_calculator.ap_dict)
+                ap_calculator.compute_metrics(batch)
+                for k in ("tp_corners", "tp_fp_corners", "tp_fn_corners", "tp_edges", "tp_fp_edges", "tp_fn_edges"):
+                    assert int(ap_calculator.ap_dict[k] - before[k]) == int(want[k]), k
+                assert ap_calculator.ap_dict["distance"] - before["distance"] == pytest.approx(want["distance"], rel=1e-12, abs=1e-14)
+                assert ap_calculator.ap_dict["wed"] - before["wed"] == pytest.approx(want["wed"], rel=1e-6, abs=1e-9)
     with contextlib.redirect_stdout(io.StringIO()) as text:
         ap_calculator.output_accuracy()
     assert "Corners Precision" in text.getvalue()
     d = ap_calculator.ap_dict
-    assert d["tp_fn_corners"] == len(gts_v[0]) and d["tp_fp_corners"] == max_vertices
+    assert d["tp_fn_corners"] == 6 + 9 + 12 and d["tp_fp_corners"] == 3 * max_vertices
     assert 0.0 <= d["corners_recall"] <= 1.0 and np.isfinite(d["average_wed"])
