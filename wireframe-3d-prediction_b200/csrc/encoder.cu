@@ -3,6 +3,8 @@
 // staging casts, and the four pooled reductions with their backward.
 #include "wf_common.cuh"
 
+#include <stdlib.h>
+
 #include <math_constants.h>
 #include <type_traits>
 
@@ -267,8 +269,8 @@ __device__ __forceinline__ void prologue(Smem& s, const float* __restrict__ W, c
     v[8] = bb[0] + bb[1];
     block_sum<9>(s, v, o);
 #pragma unroll
-    for (int k = 0; k < D; ++k) { const float m = o[k] * (1.0f / C); w[0][k] -= m; w[1][k] -= m; }
-    { const float m = o[8] * (1.0f / C); bb[0] -= m; bb[1] -= m; }
+    for (int k = 0; k < D; ++k) { const float m = o[k] * (1.0f / C); w[0][k] -= m; w[1][k] -= m; if (t == 0) s.cm[k] = m; }
+    { const float m = o[8] * (1.0f / C); bb[0] -= m; bb[1] -= m; if (t == 0) s.cm[8] = m; }
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < 9; ++i)
@@ -484,6 +486,140 @@ bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float
 
 }  // namespace l1c
 
+// ------------------------------------------------------------------------------------------
+// layer 1 forward on the legacy tensor-core path (mma.sync m16n8k8, TF32 operands, fp32 accumulate) with the 3xTF32
+// split: x = x_hi + x_lo, W = W_hi + W_lo (each part exactly representable in TF32), z = x_lo W_hi + x_hi W_lo + x_hi W_hi
+// -- fp32-grade products (error ~2^-21 of each term), which the un-normalised intensity column needs.
+// The channel-stationary SIMT kernel above waits on the FMA pipe (8 packed FMAs per channel pair and point); here a warp
+// owns 64 channels (8 n-tiles) for every staged point: weight fragments, bias, gain and shift live in ~80 registers, a
+// group of 16 points costs 8 + 2 shared loads, 24 MMAs and a packed epilogue.  LayerNorm statistics as in l1c (centred layer
+// + Cholesky factor, rstd per point computed once while staging).
+// ------------------------------------------------------------------------------------------
+namespace l1m {
+
+constexpr int C = l1c::C, D = l1c::D, NT = l1c::NT, PB = l1c::PB, XS = 12;       // XS: padded row stride of the staged points (bank-conflict free)
+typedef unsigned long long u64;
+
+struct Smem {
+    l1c::Smem base;          // prologue scratch, Cholesky factor R, column means
+    float xh[PB][XS];        // staged points, TF32 "big" parts
+    float xl[PB][XS];        // TF32 "small" parts
+    float rs[PB];            // rstd per staged point (0 for rows beyond M)
+};
+
+__device__ __forceinline__ float tf32_rn(float v) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int HDT>
+__global__ void __launch_bounds__(NT, 2)
+fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ g,
+           const float* __restrict__ be, void* __restrict__ h, int M, float eps) {
+    __shared__ Smem s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, gid = lane >> 2, tig = lane & 3;
+    {
+        u64 w2[D], b2;                                      // the prologue's own per-thread weights are not needed here
+        l1c::prologue(s.base, W, b, w2, b2);
+    }
+    // this thread's fragments for the warp's 8 n-tiles: B[k][n] = Wt[channel n][k], k = tig / tig + 4, n = gid
+    uint32_t bh[8][2], bl[8][2];
+    u64 bias2[8], g2[8], be2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int chb = warp * 64 + j * 8 + gid;                                   // B fragment column
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = tig + 4 * q;
+            const float wv = W[(size_t)chb * D + k] - s.base.cm[k];
+            const float hi = tf32_rn(wv);
+            bh[j][q] = __float_as_uint(hi); bl[j][q] = __float_as_uint(tf32_rn(wv - hi));
+        }
+        const int chc = warp * 64 + j * 8 + 2 * tig;                               // accumulator columns (chc, chc + 1)
+        bias2[j] = l1c::pk2(b[chc] - s.base.cm[8], b[chc + 1] - s.base.cm[8]);
+        g2[j] = l1c::pk2(g[chc], g[chc + 1]); be2[j] = l1c::pk2(be[chc], be[chc + 1]);
+    }
+    const int nblk = (M + PB - 1) / PB;
+    float4 xa = make_float4(0, 0, 0, 0), xb = xa;
+    int blk = blockIdx.x;
+    if (blk < nblk && blk * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(blk * PB + t) * D); xa = src[0]; xb = src[1]; }
+    for (; blk < nblk; blk += gridDim.x) {
+        const int p0 = blk * PB;
+        __syncthreads();                                  // previous block's readers are done with the staging buffers
+        {   // stage point p0 + t: rstd from the factor R, TF32 split of its 8 features
+            const float xv[9] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, 1.0f};
+            float var = 0.f;
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = i; j < 9; ++j) a = fmaf(s.base.R[q++], xv[j], a);
+                var = fmaf(a, a, var);
+            }
+            s.rs[t] = p0 + t < M ? rsqrtf(var + eps) : 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { const float hi = tf32_rn(xv[k]); s.xh[t][k] = hi; s.xl[t][k] = tf32_rn(xv[k] - hi); }
+        }
+        const int nb = blk + gridDim.x;                   // prefetch the next block's point while this one is processed
+        if (nb < nblk && nb * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(nb * PB + t) * D); xa = src[0]; xb = src[1]; }
+        __syncthreads();
+        const int np = min(PB, M - p0);
+        uint32_t* const otile = reinterpret_cast<uint32_t*>(&s.base.xs2[0][0]) + warp * 512;      // 16 rows x 32 words per warp
+        for (int g0 = 0; g0 < np; g0 += 16) {
+            const int ra = g0 + gid, rb = ra + 8;         // this thread's two accumulator rows (staged point indices)
+            uint32_t ah[4], al[4];
+            ah[0] = __float_as_uint(s.xh[ra][tig]); ah[1] = __float_as_uint(s.xh[rb][tig]);
+            ah[2] = __float_as_uint(s.xh[ra][tig + 4]); ah[3] = __float_as_uint(s.xh[rb][tig + 4]);
+            al[0] = __float_as_uint(s.xl[ra][tig]); al[1] = __float_as_uint(s.xl[rb][tig]);
+            al[2] = __float_as_uint(s.xl[ra][tig + 4]); al[3] = __float_as_uint(s.xl[rb][tig + 4]);
+            const float rsa = s.rs[ra], rsb = s.rs[rb];
+            const u64 rsa2 = l1c::pk2(rsa, rsa), rsb2 = l1c::pk2(rsb, rsb);
+            const bool oka = ra < np, okb = rb < np;
+            const size_t rowa = (size_t)(p0 + ra) * C, rowb = (size_t)(p0 + rb) * C;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float d[4];
+                l1c::up2(bias2[j], d[0], d[1]); d[2] = d[0]; d[3] = d[1];
+                mma_tf32(d, al, bh[j][0], bh[j][1]);      // small terms first
+                mma_tf32(d, ah, bl[j][0], bl[j][1]);
+                mma_tf32(d, ah, bh[j][0], bh[j][1]);
+                float y0, y1, y2, y3;
+                l1c::up2(l1c::fma2(l1c::mul2(l1c::pk2(d[0], d[1]), rsa2), g2[j], be2[j]), y0, y1);
+                l1c::up2(l1c::fma2(l1c::mul2(l1c::pk2(d[2], d[3]), rsb2), g2[j], be2[j]), y2, y3);
+                y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f);
+                const int ch = warp * 64 + j * 8 + 2 * tig;
+                if (HDT == WF_BF16) {
+                    // the warp's 16 x 64 bf16 tile is collected in shared memory (the l1c staging area, unused here; 4-word
+                    // groups XOR-swizzled with the row) and leaves as 128-byte row segments, not as 16-byte pieces
+                    const __nv_bfloat162 va = __floats2bfloat162_rn(y0, y1), vb = __floats2bfloat162_rn(y2, y3);
+                    const int w = j * 4 + tig;
+                    otile[gid * 32 + (w ^ ((gid & 7) << 2))] = *reinterpret_cast<const uint32_t*>(&va);
+                    otile[(gid + 8) * 32 + (w ^ ((gid & 7) << 2))] = *reinterpret_cast<const uint32_t*>(&vb);
+                } else {
+                    if (oka) reinterpret_cast<float2*>(h)[(rowa + ch) >> 1] = make_float2(y0, y1);
+                    if (okb) reinterpret_cast<float2*>(h)[(rowb + ch) >> 1] = make_float2(y2, y3);
+                }
+            }
+            if (HDT == WF_BF16) {
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int row = it * 4 + (lane >> 3), c16 = lane & 7;
+                    const uint4 v = *reinterpret_cast<const uint4*>(otile + row * 32 + ((c16 ^ (row & 7)) << 2));
+                    if (g0 + row < np)
+                        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(h) + (size_t)(p0 + g0 + row) * C + warp * 64 + c16 * 8) = v;
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+}  // namespace l1m
+
 __global__ void stats_finalize_kernel(const float2* __restrict__ st, int M, int parts, float invC, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,6 +783,14 @@ extern "C" int wf_enc_l1_fwd(const float* x, const float* W, const float* b, con
     WF_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "wf_enc_l1_fwd: x must be 16-byte aligned");
     WF_CHECK_ARG((reinterpret_cast<uintptr_t>(W) & 15) == 0, "wf_enc_l1_fwd: W must be 16-byte aligned");
     const int grid = min(cdiv(M, enc::l1c::PB), sm_count() * 2);
+    // WF_B200_L1_MMA=0 selects the channel-stationary SIMT forward instead of the 3xTF32 tensor-core one
+    static const bool l1_mma = [] { const char* e = getenv("WF_B200_L1_MMA"); return !(e && e[0] == '0'); }();
+    if (l1_mma && (h_dtype == WF_BF16 || h_dtype == WF_F32)) {
+        if (h_dtype == WF_BF16) enc::l1m::fwd_kernel<WF_BF16><<<grid, enc::l1m::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
+        else enc::l1m::fwd_kernel<WF_F32><<<grid, enc::l1m::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
     if (h_dtype == WF_BF16) enc::l1c::fwd_kernel<WF_BF16><<<grid, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
     else if (h_dtype == WF_F32) enc::l1c::fwd_kernel<WF_F32><<<grid, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
     else { set_error("wf_enc_l1_fwd: bad dtype"); return WF_EINVAL; }
