@@ -454,6 +454,11 @@ def encoder_pooled_infer(x, params, *, chunk_rows=None, index_offset=0, points_t
         raise _lib.WfError(f"encoder_pooled_infer needs >= {_FUSED_MIN_POINTS} points per cloud (got {N})")
     chunk = INFER_CHUNK_ROWS if chunk_rows is None else int(chunk_rows)
     chunk = max(128, (min(chunk, M) + 127) // 128 * 128)
+    if chunk_rows is None and M > chunk:
+        # equal chunks instead of full ones plus a remainder (640 000 rows: 2 x 320 000, not 524 288 + 115 712): the short
+        # tail ran the persistent GEMMs at a fraction of a wave; rounded to the 256-row cluster tile
+        n_chunks = -(-M // chunk)
+        chunk = min(chunk, (-(-M // n_chunks) + 255) // 256 * 256)
     mask, cnt = point_mask(x)                                  # cnt = max(#valid, 1)
     layers = ((W2, b2, g2, be2), (W3, b3, g3, be3), (W4, b4, g4, be4))
     wbs = [cast_bf16(W) for (W, _, _, _) in layers]
