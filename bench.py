@@ -28,13 +28,22 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "wireframe-3d-prediction_b200")
-for p in (PKG, ROOT):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")          # the unmodified reference (oracle/make_ref.py), git-ignored
+REFERENCE_ARM = any(a == "--impl=reference" or (a == "--impl" and sys.argv[i + 1:i + 2] == ["reference"])
+                    for i, a in enumerate(sys.argv))
+if REFERENCE_ARM:
+    # the reference arm never imports the product: `models` / `losses` resolve to the reference's own packages
+    sys.path.insert(0, ROOT)
+    if os.path.isdir(os.path.join(REF_DIR, "models")):
+        sys.path.insert(0, REF_DIR)
+else:
+    for p in (PKG, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
 
 # stdout must carry exactly one JSON line, but libraries write there too (NCCL prints its version banner to stdout at
-# NCCL_DEBUG=VERSION and above): keep the real stdout aside and point fd 1 at stderr for the whole run.
-os.environ.pop("NCCL_DEBUG", None)
+# NCCL_DEBUG=VERSION and above): keep the real stdout aside and point fd 1 at stderr for the whole run.  NCCL_DEBUG itself
+# is left as the caller set it (the driver reads the ranks' NCCL lines from stderr).
 sys.stdout.flush()
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
@@ -59,10 +68,18 @@ def workload_name(n_gpus):
             f"counts~U{{16..64}}, global batch {PER_GPU_BATCH * n_gpus} (BASELINE.json configs[2], weak scaling)")
 
 
+def _synthetic():
+    """wf_b200/synthetic.py loaded by path (pure numpy/torch): the reference arm must not import the product package."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_wf_synthetic", os.path.join(PKG, "wf_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_batch(rank, B):
     """Synthetic batch shaped like datasets/building3d.py:109-126 output + train.py:48-88 targets."""
-    from wf_b200.synthetic import make_inputs
-    return make_inputs(seed=rank, B=B, N=POINTS, V=VERTS, min_count=16, max_count=64)
+    return _synthetic().make_inputs(seed=rank, B=B, N=POINTS, V=VERTS, min_count=16, max_count=64)
 
 
 class ClockSampler:
@@ -163,54 +180,123 @@ def traffic_from_profile():
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (torch CPU restatement of the reference path), all host threads
+# Reference arm: the UNMODIFIED reference (oracle/_ref, copied by oracle/make_ref.py) through its own public API --
+# PointCloudToWireframe.forward, WireframeLoss, the body of train.py:124-142 -- on the host cores (default) or, for the
+# `gpu_eager_baseline` field, as PyTorch eager on the B200.  Falls back to the oracle port (CPU only) when oracle/_ref is absent.
 # ----------------------------------------------------------------------------------------------
-def cpu_step_factory(sample_b):
-    from oracle import wireframe_oracle as wo
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = {k: v.clone().requires_grad_(True) for k, v in wo.make_state_dict(0, VERTS).items()}
-    opt = torch.optim.Adam([v for k, v in sd.items() if "spatial_proj" not in k], lr=1e-3, weight_decay=1e-6)
-    x, tgt, _ = wo.make_inputs(0, sample_b, POINTS, VERTS, min_count=16, max_count=64)
+CPU_SAMPLE_B = 8            # clouds per CPU step: a bounded sample of the 64-cloud step (~2 s/step on 16 cores, ~3 GB)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        ld, _ = wo.train_step(sd, x, tgt, max_vertices=VERTS)
-        torch.nn.utils.clip_grad_norm_([v for v in sd.values() if v.grad is not None], 1.0)
+
+def reference_step_factory(device, sample_b, tf32=False):
+    have_ref = os.path.isdir(os.path.join(REF_DIR, "models"))
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    else:
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+        torch.backends.cudnn.allow_tf32 = bool(tf32)
+    x, tgt, counts = make_batch(0, sample_b)
+    if not have_ref:
+        if dev.type != "cpu":
+            raise SystemExit("oracle/_ref missing: the eager-GPU baseline needs the reference's own modules")
+        from oracle import wireframe_oracle as wo
+        sd = {k: v.clone().requires_grad_(True) for k, v in wo.make_state_dict(0, VERTS).items()}
+        opt = torch.optim.Adam([v for k, v in sd.items() if "spatial_proj" not in k], lr=1e-3, weight_decay=1e-6)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            ld, _ = wo.train_step(sd, x, tgt, max_vertices=VERTS)
+            torch.nn.utils.clip_grad_norm_([v for v in sd.values() if v.grad is not None], 1.0)
+            opt.step()
+            return float(ld["total_loss"].detach())
+        return step, "port"
+    from models.PointCloudToWireframe import PointCloudToWireframe      # the reference's (sys.path: oracle/_ref first)
+    from losses.WireframeLoss import WireframeLoss
+    assert os.path.realpath(sys.modules["models.PointCloudToWireframe"].__file__).startswith(os.path.realpath(REF_DIR))
+    torch.manual_seed(0)
+    model = PointCloudToWireframe(input_dim=FEATS, max_vertices=VERTS).to(dev)          # train.py:40
+    model.train()
+    crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)      # train.py:90-94
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-6)              # train.py:96 (before the first forward)
+    x = x.to(dev)
+    tgt = {k: v.to(dev) for k, v in tgt.items()}
+    counts = tgt["vertex_counts"]
+
+    def step():                                                                         # train.py:124-145
+        opt.zero_grad()
+        pred = model(x, counts)
+        ld = crit(pred, tgt)
+        ld["total_loss"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
         opt.step()
-        return float(ld["total_loss"].detach())
-    return step
+        return ld["total_loss"].item()
+    return step, "reference"
 
 
-def run_cpu(steps, warmup, sample_b):
-    step = cpu_step_factory(sample_b)
+def run_reference(device, steps, warmup, sample_b, tf32=False):
+    step, kind = reference_step_factory(device, sample_b, tf32)
+    cuda = torch.device(device).type == "cuda"
     for _ in range(warmup):
         step()
+    if cuda:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
+    if cuda:
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return sample_b * steps / dt, dt / steps * 1e3
+    return sample_b * steps / dt, dt / steps * 1e3, kind
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return                                   # rank 0 alone runs the CPU arm
-    sample_b = 2
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
-    val, ms = run_cpu(steps, warmup, sample_b)
+        return                                   # rank 0 alone runs the reference arm
+    if args.ref_device == "cuda":
+        # PyTorch eager on the B200 (SURVEY 8d "the real bar"): the full 64-cloud step, fp32 or TF32-allowed
+        sample_b = args.ref_batch or PER_GPU_BATCH
+        steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+        val, ms, kind = run_reference("cuda", steps, warmup, sample_b, tf32=args.ref_tf32)
+        emit({"impl": "reference", "device": "cuda", "metric": METRIC, "value": val, "unit": UNIT, "ms_per_step": ms,
+              "steps": steps, "warmup": warmup, "batch": sample_b, "kind": kind, "tf32": bool(args.ref_tf32),
+              "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0),
+              "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30})
+        return
+    sample_b = args.ref_batch or CPU_SAMPLE_B
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    val, ms, kind = run_reference("cpu", steps, warmup, sample_b)
     cores = os.cpu_count() or 1
+    what = "the unmodified reference (oracle/_ref) through its own module API" if kind == "reference" else "oracle port"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "note": "CPU arm: bounded sample per step"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample_b} clouds x {POINTS} pts per step (full fwd+loss+bwd+clip+Adam), "
-                                   f"{steps} steps after {warmup} warm-up, torch {torch.__version__} CPU, {cores} threads"},
+        "config": {"workload": workload_name(args.gpus),
+                   "note": f"CPU arm: {what}; bounded sample of {sample_b} clouds per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample_b} clouds x {POINTS} pts per step (zero_grad, forward, loss incl. scipy matching, "
+                                   f"backward, clip, Adam: train.py:124-142), {steps} steps after {warmup} warm-up, "
+                                   f"torch {torch.__version__} CPU, {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+def reference_subprocess(extra, timeout=900):
+    """Run a reference leg in its own process (its `models`/`losses` packages shadow the product's by name) and return its
+    JSON line, or {"unavailable": why}."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference"] + extra
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            tail = r.stderr.strip().splitlines()[-1] if r.stderr.strip() else "no output"
+            return {"unavailable": f"rc={r.returncode}: {tail}"[:300]}
+        return json.loads(lines[-1])
+    except Exception as e:                                    # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -246,6 +332,7 @@ def main_gpu(args):
     x = x_pin.to(dev, non_blocking=True)
     tgt = {k: v.to(dev, non_blocking=True) for k, v in tgt_pin.items()}
     counts = tgt["vertex_counts"]
+    host_counts = [int(c) for c in counts_host.tolist()]
     all_counts = [make_counts_only(r, B) for r in range(world)]
     wv, wx, we = shard_loss_weights(counts_host.tolist(), all_counts, VERTS)
 
@@ -294,6 +381,8 @@ def main_gpu(args):
             ev = torch.cuda.Event(); ev.record(copy_stream)
             for t in tg.values():
                 ops.mark_ready(t, ev)             # as wf_b200.targets.DevicePrefetcher tags what it stages
+            # ... and the host's own copy of the counts travels with the device one (no read-back inside the step)
+            tg["vertex_counts"]._wf_host_counts = (tg["vertex_counts"]._version, tuple(host_counts))
         return xs, tg, ev
 
     def timed(n, e2e):
@@ -328,7 +417,9 @@ def main_gpu(args):
     # Warm-up.  With more than one rank the first ~15 steps after start-up carry isolated 10-100 ms stalls on one rank
     # (seen at 2, 4 and 8 GPUs with and without clock sampling or per-launch events, never later: diagnosis in DESIGN.md section 4),
     # so multi-GPU runs settle for 20 further untimed steps; the JSON line reports the warm-up actually done.
-    n_warm = max(args.warmup, 3) + (20 if world > 1 else 0)
+    # Every run also settles into the sustained power state first: inside a cold 20-step region the step time drifted by ~10 %
+    # (r01: 22.4 -> 24.8 ms) as the package reached its power cap, so a short region flattered the steady state.
+    n_warm = max(args.warmup, 3) + (30 if world > 1 else 20)
     for _ in range(n_warm):
         step(x, tgt, False)
     barrier()
@@ -391,12 +482,25 @@ def main_gpu(args):
                          "flop_per_launch_avg": gemm_flop / max(1, len(prof)),
                          "encoder_train_mpts_per_s": (B * POINTS * args.steps) / (ms * 1e-3) / 1e6},
         }
+        sm = step_ms[False]
+        if len(sm) >= 4:
+            h = min(10, len(sm) // 2)
+            line["step_ms_first_last"] = {"first": round(sum(sm[:h]) / h, 3), "last": round(sum(sm[-h:]) / h, 3), "n": h}
         if world == 1 and not args.no_cpu:
-            v, cms = run_cpu(steps=3, warmup=1, sample_b=2)
-            cores = os.cpu_count() or 1
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"oracle port, 2 clouds x {POINTS} pts per step, 3 steps after 1 warm-up "
-                                              f"({cms:.0f} ms/step), torch CPU {cores} threads"}
+            # baselines, each in its own process after the timed regions (their `models` package shadows ours by name)
+            del flush
+            torch.cuda.empty_cache()
+            r = reference_subprocess(["--steps", "3", "--warmup", "1"])
+            line["cpu_baseline"] = r.get("cpu_baseline", r)
+            if not args.no_eager:
+                eager = {}
+                for name, extra in (("fp32", []), ("tf32", ["--ref-tf32"])):
+                    e = reference_subprocess(["--ref-device", "cuda", "--steps", "5", "--warmup", "2"] + extra)
+                    eager[name] = {k: e[k] for k in ("value", "ms_per_step", "batch", "kind", "peak_mem_gb", "unavailable") if k in e}
+                line["gpu_eager_baseline"] = {
+                    "what": "the unmodified reference modules as PyTorch eager on this B200 (cuBLAS/ATen kernels, per-sample "
+                            "Python loops, scipy matching on the host): the same 64 x 10,000-point train step (train.py:124-142)",
+                    "unit": UNIT, **eager}
         emit(line)
         print("per-step ms (device-resident):", step_ms[False], "\nper-step ms (e2e):", step_ms[True], file=sys.stderr)
     if world > 1:
@@ -414,7 +518,11 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="wf_b200", choices=["wf_b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and gpu_eager_baseline legs")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="reference arm: host cores (default) or eager on the GPU")
+    ap.add_argument("--ref-batch", type=int, default=0, help="reference arm: clouds per step (default 8 on CPU, 64 on the GPU)")
+    ap.add_argument("--ref-tf32", action="store_true", help="reference arm on the GPU: allow TF32 matmuls")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

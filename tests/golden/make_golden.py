@@ -31,6 +31,7 @@ from losses.WireframeLoss import WireframeLoss  # noqa: E402
 from oracle import wireframe_oracle as wo  # noqa: E402
 
 torch.set_num_threads(8)
+GSAMP = 1024
 
 
 def build_reference(seed, V, train_mode):
@@ -63,12 +64,16 @@ def grad_digest(named_params):
         g = p.grad.detach().double().reshape(-1)
         out["gnorm/" + k] = np.array([g.norm().item(), g.sum().item()], np.float64)
         out["ghead/" + k] = g[:16].float().numpy()
+        # element-wise reference values on a fixed stride (<= GSAMP entries per parameter): the bf16 tests compare these
+        # one by one with the reference's matching injected
+        out["gsamp/" + k] = g[::max(1, -(-g.numel() // GSAMP))].float().numpy()
     return out
 
 
-def case_train(name, seed, B, N, V, pad_frac=0.0, norm_intensity=True):
+def case_train(name, seed, B, N, V, pad_frac=0.0, norm_intensity=True, min_count=2, max_count=None, store_dx=True):
     m, _ = build_reference(seed, V, True)
-    x, tgt, counts = wo.make_inputs(seed, B, N, V, pad_frac=pad_frac, norm_intensity=norm_intensity)
+    x, tgt, counts = wo.make_inputs(seed, B, N, V, pad_frac=pad_frac, norm_intensity=norm_intensity, min_count=min_count,
+                                    max_count=max_count)
     xr = x.clone().requires_grad_(True)
     crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)
     pred = m(xr, counts)
@@ -77,6 +82,7 @@ def case_train(name, seed, B, N, V, pad_frac=0.0, norm_intensity=True):
     ld["total_loss"].backward()
     out = {
         "meta": np.array([seed, B, N, V, int(pad_frac * 1000), int(norm_intensity)], np.int64),
+        "count_range": np.array([min_count, -1 if max_count is None else max_count], np.int64),
         "vertices": pred["vertices"].detach().numpy(),
         "existence": pred["existence_probabilities"].detach().numpy(),
         "edge_probs": pred["edge_probs"].detach().numpy(),
@@ -85,7 +91,8 @@ def case_train(name, seed, B, N, V, pad_frac=0.0, norm_intensity=True):
         "n_edges": np.array([len(e) for e in pred["edge_indices"]], np.int64),
         "losses": np.array([ld[k].item() for k in ("total_loss", "vertex_loss", "existence_loss",
                                                     "edge_loss")], np.float64),
-        "dx": xr.grad.numpy(),
+        # large clouds: the first 64 points of every cloud only (the fixture stays small)
+        "dx": xr.grad.numpy() if store_dx else xr.grad[:, :64].numpy(),
     }
     for b, (pi, ti) in enumerate(matched):
         out[f"match_p/{b}"] = np.asarray(pi, np.int64)
@@ -96,18 +103,29 @@ def case_train(name, seed, B, N, V, pad_frac=0.0, norm_intensity=True):
         out["pf_max"] = pf.max(dim=1).values.numpy()
         out["pf_argmax"] = pf.max(dim=1).indices.numpy()
         out["pf_mean"] = pf.mean(dim=1).numpy()
+        # gap between the largest and second-largest value per (cloud, channel): the argmax is only well defined where it
+        # exceeds fp32 rounding noise
+        top2 = pf.topk(2, dim=1).values
+        out["pf_top2_gap"] = (top2[:, 0] - top2[:, 1]).numpy()
     out.update(grad_digest(m.named_parameters()))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "losses", out["losses"], "counts", counts.tolist())
 
 
-def case_eval(name, seed, B, N, V):
-    m, _ = build_reference(seed, V, False)
+def case_eval(name, seed, B, N, V, exist_bias=None):
+    m, sd = build_reference(seed, V, False)
+    if exist_bias is not None:
+        # random-init existence logits hover around 0; push slot k's logit by exist_bias[k] so that the eval-mode counts
+        # (#slots with p > 0.5, models/VertexPredictor.py:124-127) are neither 0/1 (IndexError) nor all V
+        sd = {k: v.clone() for k, v in sd.items()}
+        sd["vertex_predictor.final_layer.bias"].view(V, 4)[:, 3] += torch.as_tensor(exist_bias, dtype=torch.float32)
+        m.load_state_dict(sd, strict=True)
     x, tgt, counts = wo.make_inputs(seed, B, N, V, norm_intensity=True)
     with torch.no_grad():
         pred = m(x, counts)
     out = {
         "meta": np.array([seed, B, N, V, 0, 1], np.int64),
+        "exist_bias": np.zeros(0, np.float32) if exist_bias is None else np.asarray(exist_bias, np.float32),
         "vertices": pred["vertices"].numpy(),
         "existence": pred["existence_probabilities"].numpy(),
         "edge_probs": pred["edge_probs"].numpy(),
@@ -172,6 +190,27 @@ def case_loss_ties(name, seed):
     print(name, "ok")
 
 
+def case_hungarian_rmse(name, seed):
+    """models/utils.py:38-55 (fp64 cdist + fp64 LSAP): random, rectangular both ways, and grid-snapped (tied) vertex sets."""
+    from models.utils import hungarian_rmse
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {"meta": np.array([seed], np.int64)}
+    shapes = [(5, 5), (12, 7), (7, 12), (1, 4), (38, 38), (64, 20), (16, 16), (9, 9)]
+    vals = []
+    for k, (a, b) in enumerate(shapes):
+        p = rng.uniform(-1, 1, (a, 3)); t = rng.uniform(-1, 1, (b, 3))
+        if k >= 6:                                       # heavy ties: coordinates on a coarse grid
+            p = np.round(p * 2) / 2; t = np.round(t * 2) / 2
+        if k == 7:
+            p = p.astype(np.float32); t = t.astype(np.float32)
+        out[f"p/{k}"] = p; out[f"t/{k}"] = t
+        vals.append(hungarian_rmse(p, t))
+    out["rmse"] = np.asarray(vals, np.float64)
+    out["empty"] = np.array([hungarian_rmse(np.zeros((0, 3)), np.zeros((0, 3))), hungarian_rmse(np.zeros((0, 3)), np.ones((2, 3)))])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, out["rmse"], out["empty"])
+
+
 if __name__ == "__main__":
     case_train("train_b2_n384_v12", seed=3, B=2, N=384, V=12)
     case_train("train_b3_n300_v20_pad", seed=5, B=3, N=300, V=20, pad_frac=0.1)
@@ -179,6 +218,10 @@ if __name__ == "__main__":
     case_eval("eval_b2_n256_v16", seed=11, B=2, N=256, V=16)
     case_matchers("matchers", seed=13)
     case_loss_ties("loss_ties", seed=17)
+    # BASELINE.json's real shapes (configs[1]/[2]): 10,000-point clouds, 64 vertex slots, counts ~ U{16..64}
+    case_train("train_b2_n10000_v64", seed=23, B=2, N=10000, V=64, min_count=16, max_count=64, store_dx=False)
+    case_eval("eval_b2_n10000_v64", seed=29, B=2, N=10000, V=64, exist_bias=np.linspace(3.0, -3.0, 64))
+    case_hungarian_rmse("hungarian_rmse", seed=31)
 
 
 def case_real_building(name, seed, index=0):

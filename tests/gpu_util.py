@@ -26,3 +26,16 @@ def col_to_pairs(col, nr, nc):
     c = np.asarray(col[:nr])
     rows = np.nonzero(c >= 0)[0] if nc < nr else np.arange(nr)
     return rows.astype(np.int64), c[rows].astype(np.int64)
+
+
+def record(test, **vals):
+    """Append the errors a parity test OBSERVED to gpurun_out/parity_observed.jsonl (when that directory exists): the
+    asserted tolerances are set from these records (<= 10x observed) and the file is copied to profiles/ per round."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    with open(os.path.join(d, "parity_observed.jsonl"), "a") as f:
+        f.write(json.dumps({"test": test, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in vals.items()}}) + "\n")

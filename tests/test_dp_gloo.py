@@ -158,7 +158,8 @@ def _pool_worker(rank, world, port, q):
     hsum = torch.stack([vals[..., :K].sum(1), (vals[..., :K] * mask.unsqueeze(-1)).sum(1)])
     cnt = mask.sum(1).float()
     reduce_pool_shards(packed, hsum, cnt)
-    q.put((rank, packed, hsum, cnt, vals, mask))
+    # by value (numpy): torch tensors travel through a Queue as shared-memory handles that die with this process
+    q.put((rank, packed.numpy(), hsum.numpy(), cnt.numpy(), vals.numpy(), mask.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -169,10 +170,11 @@ def test_point_sharded_pool_reduce_gloo():
     import numpy as np
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 200
+    port = _free_port()
     ps = [ctx.Process(target=_pool_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in ps]
     res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    res = [(r[0], *[torch.from_numpy(a) for a in r[1:]]) for r in res]
     [p.join(timeout=60) for p in ps]
     allv = torch.cat([res[0][4], res[1][4]], dim=1); allm = torch.cat([res[0][5], res[1][5]], dim=1)
     for r in range(2):

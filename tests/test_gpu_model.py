@@ -1,9 +1,10 @@
 """End-to-end GPU parity through the drop-in module API (models.PointCloudToWireframe, losses.WireframeLoss,
 matchers) against the golden fixtures generated from the unmodified reference and against the oracle.
 
-fp32 mode: the bar is BASELINE.json's 1e-5-relative class (we assert 2e-4 scale-relative on outputs and
-2e-3 on gradients: fp32 summation order differs between ATen-CPU and our kernels across 30M-parameter
-reductions); matchings and counts must be identical.  bf16 mode: stated tolerance 5e-2 scale-relative."""
+fp32 mode: BASELINE.json's 1e-5-relative class -- outputs and losses 2e-5, gradient norms 5e-5, gradient entries 2e-4
+(scale-relative; the reference's own run-to-run reproducibility on its CPU path is 1.4e-5 on a gradient entry); matchings,
+counts and decided argmax indices identical.  bf16 mode (production): outputs 1e-2, gradients element-wise 5e-2 with the
+reference's assignment injected.  Observed values: profiles/r02_parity_observed.jsonl."""
 import os
 
 import numpy as np
@@ -14,7 +15,7 @@ from gpu_util import assert_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
-TRAIN = ["train_b2_n384_v12", "train_b3_n300_v20_pad", "train_b1_n256_v8_rawint"]
+TRAIN = ["train_b2_n384_v12", "train_b3_n300_v20_pad", "train_b1_n256_v8_rawint", "train_b2_n10000_v64"]
 
 
 def _model(seed, V, train):
@@ -33,40 +34,74 @@ def _model(seed, V, train):
     return m
 
 
+# Tolerances (scale-relative max error unless noted).  Each is <= 10x the error observed on a B200 (profiles/r02_parity_observed.jsonl,
+# written by gpu_util.record) and the fp32 gradient ones cannot go below the reference's OWN reproducibility: two runs of the
+# unmodified reference on this container's 8 threads differ by up to 1.4e-5 on a gradient entry and 1e-5 on a gradient norm
+# (MKL summation order; measured while regenerating the fixtures).
+TOL = {
+    "fp32": dict(out=2e-5, loss=2e-5, gnorm=5e-5, gelem=2e-4, dx=2e-4),
+    "bf16": dict(out=1e-2, loss=5e-3, gnorm=3e-2, gelem=5e-2, dx=None),
+}
+
+
+def _ref_col(g, B, V):
+    """The reference's assignment as the loss kernels take it: col_of_row[b, pred slot] = target index, -1 = unmatched."""
+    col = torch.full((B, V), -1, dtype=torch.int32)
+    for b in range(B):
+        col[b, torch.from_numpy(g[f"match_p/{b}"])] = torch.from_numpy(g[f"match_t/{b}"]).to(torch.int32)
+    return col
+
+
 @pytest.mark.parametrize("name", TRAIN)
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_train_step_vs_reference_golden(golden_dir, name, prec):
+    """One training step through the drop-in modules against the UNMODIFIED reference's outputs, losses, matching, argmax and
+    all 80 parameter gradients (norm + 16 leading + <=1024 strided entries each) -- incl. BASELINE.json's real shape
+    (2 clouds x 10,000 points, 64 vertex slots, counts ~ U{16..64}).
+    fp32 mode: matchings, counts identical; argmax identical wherever the reference's top-2 gap exceeds 1e-5*|max|.
+    bf16 mode: gradients are compared ELEMENT-WISE with the reference's matching injected, so a flipped assignment (a
+    legitimate discontinuity under bf16-sized perturbations) cannot hide an error; the flip rate itself is recorded."""
     from oracle import wireframe_oracle as wo
     from wf_b200 import ops
     from losses.WireframeLoss import WireframeLoss
+    from gpu_util import record
     g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     seed, B, N, V, pad, norm_i = [int(v) for v in g["meta"]]
+    cmin, cmax = [int(v) for v in g["count_range"]]
+    tol = TOL[prec]
+    rawint = "rawint" in name
     ops.set_precision(prec)
     try:
         m = _model(seed, V, True)
-        x, tgt, counts = wo.make_inputs(seed, B, N, V, pad_frac=pad / 1000.0, norm_intensity=bool(norm_i))
+        x, tgt, counts = wo.make_inputs(seed, B, N, V, pad_frac=pad / 1000.0, norm_intensity=bool(norm_i), min_count=cmin,
+                                        max_count=None if cmax < 0 else cmax)
         xg = x.cuda().requires_grad_(True)
         tg = {k: v.cuda() for k, v in tgt.items()}
         pred = m(xg, counts.cuda())
         crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)
+        ours = crit._hungarian_matching(pred, tg)
+        same_pairs = sum(int(np.array_equal(pi, g[f"match_p/{b}"]) and np.array_equal(ti, g[f"match_t/{b}"]))
+                         for b, (pi, ti) in enumerate(ours))
+        if prec == "fp32":
+            assert same_pairs == B, "fp32 matching differs from the reference's"
+        else:
+            ref_col = _ref_col(g, B, V).cuda()
+            crit._match_device = lambda predictions, targets, sync=None: ref_col      # the reference's assignment, injected
         ld = crit(pred, tg)
         ld["total_loss"].backward()
-        # bf16: the Hungarian matching may legitimately flip for near-tied costs, which changes head gradients
-        # discontinuously -> end-to-end bf16 gradients get a loose norm check only; the bf16 encoder gradients are
-        # checked tightly with fixed upstream gradients in test_gpu_tc.py::test_encoder_tc_vs_fp32_path
-        otol, gtol = (2e-4, 2e-3) if prec == "fp32" else (5e-2, 2.5e-1)
-        assert_close(pred["vertices"], torch.from_numpy(g["vertices"]), otol, "vertices")
-        assert_close(pred["existence_probabilities"], torch.from_numpy(g["existence"]), otol, "existence")
-        assert_close(pred["edge_probs"], torch.from_numpy(g["edge_probs"]), otol, "edge_probs")
-        assert_close(pred["global_features"], torch.from_numpy(g["global_features"]), otol, "global_features")
+        obs = {"matching_identical_samples": same_pairs, "samples": B}
+        obs["vertices"] = assert_close(pred["vertices"], torch.from_numpy(g["vertices"]), tol["out"], "vertices")
+        obs["existence"] = assert_close(pred["existence_probabilities"], torch.from_numpy(g["existence"]), tol["out"], "existence")
+        obs["edge_probs"] = assert_close(pred["edge_probs"], torch.from_numpy(g["edge_probs"]), tol["out"], "edge_probs")
+        obs["global_features"] = assert_close(pred["global_features"], torch.from_numpy(g["global_features"]), tol["out"],
+                                              "global_features")
         assert [len(e) for e in pred["edge_indices"]] == g["n_edges"].tolist()
         got = np.array([ld[k].item() for k in ("total_loss", "vertex_loss", "existence_loss", "edge_loss")])
-        np.testing.assert_allclose(got, g["losses"], rtol=otol * 5, atol=otol)
+        obs["loss"] = float(np.max(np.abs(got - g["losses"]) / np.abs(g["losses"])))
+        np.testing.assert_allclose(got, g["losses"], rtol=tol["loss"], atol=0)
         if prec == "fp32":
             assert np.array_equal(pred["actual_vertex_counts"].cpu().numpy(), g["dyn_counts"])
-            for b, (pi, ti) in enumerate(crit._hungarian_matching(pred, tg)):
-                assert np.array_equal(pi, g[f"match_p/{b}"]) and np.array_equal(ti, g[f"match_t/{b}"])
-        worst = ("", 0.0)
+        worst_n, worst_e = ("", 0.0), ("", 0.0)
         fails = []
         for k, p in m.named_parameters():
             if "gnone/" + k in g:
@@ -75,51 +110,110 @@ def test_train_step_vs_reference_golden(golden_dir, name, prec):
             gr = p.grad.detach().double().reshape(-1).cpu()
             ref_norm = float(g["gnorm/" + k][0])
             e = abs(float(gr.norm()) - ref_norm) / max(ref_norm, 1e-12)
-            head = torch.from_numpy(g["ghead/" + k]).double()
-            scale = max(float(head.abs().max()), ref_norm / np.sqrt(gr.numel()))
-            eh = float((gr[:16] - head).abs().max()) / scale
-            print(f"  {prec} {k:55s} norm_err {e:.2e} head_err {eh:.2e}")
-            if e > worst[1]:
-                worst = (k, e)
+            samp = torch.from_numpy(g["gsamp/" + k]).double()
+            stride = max(1, -(-gr.numel() // 1024))
+            # element-wise on the strided sample; the scale is the parameter's RMS gradient entry or the sample's largest
+            scale = max(float(samp.abs().max()), ref_norm / np.sqrt(gr.numel()))
+            es = float((gr[::stride] - samp).abs().max()) / scale
+            if e > worst_n[1]:
+                worst_n = (k, e)
+            if es > worst_e[1]:
+                worst_e = (k, es)
             # un-normalised intensity (~5e4) makes the first layer's LayerNorm backward ill-conditioned
             # in fp32 (rstd ~ 1e-4, heavy cancellation): the reference's own fp32 gradient is only ~1e-2 accurate there
-            loose = 30.0 if ("rawint" in name and k.startswith("encoder.mlp.0.")) else 1.0
-            if e > gtol * loose or (prec == "fp32" and eh > gtol * 4 * loose):
-                fails.append((k, e, eh))
-        assert not fails, f"{prec} gradient mismatches: {fails[:6]} (+{max(0, len(fails) - 6)} more)"
+            loose = (600.0 if k.startswith("encoder.mlp.0.") else 20.0) if (rawint and prec == "fp32") else 1.0
+            if e > tol["gnorm"] * loose or es > tol["gelem"] * loose:
+                fails.append((k, f"norm {e:.2e}", f"elem {es:.2e}"))
+        obs["grad_norm_worst"], obs["grad_norm_worst_param"] = worst_n[1], worst_n[0]
+        obs["grad_elem_worst"], obs["grad_elem_worst_param"] = worst_e[1], worst_e[0]
         # d/d(input) is a 512-term sum with LayerNorm cancellation: not meaningful under bf16 noise, nor in fp32 with
         # un-normalised intensity (the reference's own fp32 value is noise-dominated there)
-        if prec == "fp32" and "rawint" not in name:
+        if prec == "fp32" and not rawint:
             # zero-padded points are exact duplicates: which duplicate the max-pool gradient lands on depends on last-bit
             # rounding inside the reference's MKL GEMM (all parameter gradients are unaffected) -> compare real points only
-            real = (x.abs().sum(-1) > 0)
-            assert_close(xg.grad.cpu()[real], torch.from_numpy(g["dx"])[real], gtol * 2, "dx")
-        print(prec, name, "worst grad-norm rel err", worst)
-        if prec == "fp32":        # argmax parity: identical except inside fp32 noise
+            dx_ref = torch.from_numpy(g["dx"])
+            nrow = dx_ref.shape[1]                                 # large clouds store the first 64 points of each cloud
+            real = (x[:, :nrow].abs().sum(-1) > 0)
+            obs["dx"] = assert_close(xg.grad.cpu()[:, :nrow][real], dx_ref[real], tol["dx"], "dx")
+        if prec == "fp32":        # argmax parity: identical wherever the reference's top-2 gap is above rounding noise
             r = m.encoder.pooled(xg.detach())
-            agree = (r[5].cpu().numpy() == g["pf_argmax"]).mean()
-            # raw intensity (~5e4) leaves ~1e-3 relative fp32 noise on the point features, enough to move near-tied maxima
-            assert agree > (0.9 if "rawint" in name else 0.995), f"argmax agreement {agree}"
+            # raw intensity (~5e4) leaves ~1e-3 relative fp32 noise on the point features (in the reference too)
+            thr = (2e-3 if rawint else 1e-5) * np.abs(g["pf_max"])
+            decided = g["pf_top2_gap"] > thr
+            same = r[5].cpu().numpy() == g["pf_argmax"]
+            obs["argmax_decided_fraction"] = float(decided.mean())
+            obs["argmax_agree_undecided"] = float(same[~decided].mean()) if (~decided).any() else 1.0
+            assert same[decided].all(), f"argmax differs on {int((~same[decided]).sum())} decided (cloud, channel) pairs"
+            obs["pf_max"] = assert_close(r[2], torch.from_numpy(g["pf_max"]), tol["out"] * (100 if rawint else 1), "pooled max")
+        record(f"train_step/{name}/{prec}", **obs)
+        print(prec, name, obs)
+        assert not fails, f"{prec} gradient mismatches: {fails[:6]} (+{max(0, len(fails) - 6)} more)"
     finally:
         ops.set_precision("bf16")
 
 
-def test_eval_forward_vs_reference_golden(golden_dir):
+def test_counts_of_fresh_tensors_are_never_stale():
+    """ADVICE r1 (high): a fresh counts tensor per batch gets the previous batch's recycled device address with version 0;
+    the edge head must still run with ITS counts (edge_probs width, edge_indices) -- through freshly allocated tensors."""
     from oracle import wireframe_oracle as wo
     from wf_b200 import ops
-    g = dict(np.load(os.path.join(golden_dir, "eval_b2_n256_v16.npz")))
-    seed, B, N, V = [int(v) for v in g["meta"][:4]]
     ops.set_precision("fp32")
     try:
+        V = 12
+        m = _model(3, V, True)
+        x, _, _ = wo.make_inputs(3, 2, 256, V, norm_intensity=True)
+        xg = x.cuda()
+        ptrs = set()
+        for step, cs in enumerate(([5, 7], [9, 3], [2, 12], [6, 6], [11, 4])):
+            c = torch.tensor(cs).cuda()                       # fresh tensor each step
+            ptrs.add(c.data_ptr())
+            out = m(xg, c)
+            assert [len(e) for e in out["edge_indices"]] == [k * (k - 1) // 2 for k in cs], (step, cs)
+            assert out["edge_probs"].shape[1] == max(k * (k - 1) // 2 for k in cs)
+            del c, out
+        # in-place update of ONE tensor (version bump) is seen too
+        c = torch.tensor([5, 7]).cuda()
+        m(xg, c)
+        c.copy_(torch.tensor([4, 8]))
+        assert [len(e) for e in m(xg, c)["edge_indices"]] == [6, 28]
+        print("distinct device addresses over 5 fresh count tensors:", len(ptrs))
+    finally:
+        ops.set_precision("bf16")
+
+
+@pytest.mark.parametrize("name", ["eval_b2_n256_v16", "eval_b2_n10000_v64"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_eval_forward_vs_reference_golden(golden_dir, name, prec):
+    """evaluate.py:71 (eval mode, no_grad, counts from the existence probabilities) against the unmodified reference, incl.
+    BASELINE.json configs[1]'s shape (10,000-point clouds, 64 vertex slots; the existence bias of the fixture spreads the
+    probabilities so that the data-dependent counts are 32 of 64).  bf16 takes the chunked inference encoder."""
+    from oracle import wireframe_oracle as wo
+    from wf_b200 import ops
+    from gpu_util import record
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    seed, B, N, V = [int(v) for v in g["meta"][:4]]
+    ops.set_precision(prec)
+    try:
         m = _model(seed, V, False)
+        if g["exist_bias"].size:
+            with torch.no_grad():
+                m.vertex_predictor.final_layer.bias.view(V, 4)[:, 3] += torch.from_numpy(g["exist_bias"]).cuda()
         x, tgt, counts = wo.make_inputs(seed, B, N, V, norm_intensity=True)
         with torch.no_grad():
             pred = m(x.cuda(), counts.cuda())
-        assert np.array_equal(pred["actual_vertex_counts"].cpu().numpy(), g["dyn_counts"])
-        assert_close(pred["vertices"], torch.from_numpy(g["vertices"]), 2e-4, "vertices")
-        assert_close(pred["edge_probs"], torch.from_numpy(g["edge_probs"]), 2e-4, "edge_probs")
-        assert np.array_equal(np.asarray(pred["edge_indices"][0]), g["edge_indices0"])
-        assert pred["edge_probs"].shape == tuple(g["edge_probs"].shape)
+        otol = TOL[prec]["out"]
+        # counts are a threshold on the existence probabilities: identical in fp32; in bf16 wherever no probability sits
+        # within the tolerance of 0.5
+        near = np.abs(g["existence"] - 0.5) < (1e-5 if prec == "fp32" else 2e-2)
+        if not near.any():
+            assert np.array_equal(pred["actual_vertex_counts"].cpu().numpy(), g["dyn_counts"])
+        obs = {"vertices": assert_close(pred["vertices"], torch.from_numpy(g["vertices"]), otol, "vertices"),
+               "existence": assert_close(pred["existence_probabilities"], torch.from_numpy(g["existence"]), otol, "existence")}
+        if np.array_equal(pred["actual_vertex_counts"].cpu().numpy(), g["dyn_counts"]):
+            obs["edge_probs"] = assert_close(pred["edge_probs"], torch.from_numpy(g["edge_probs"]), otol, "edge_probs")
+            assert np.array_equal(np.asarray(pred["edge_indices"][0]), g["edge_indices0"])
+            assert pred["edge_probs"].shape == tuple(g["edge_probs"].shape)
+        record(f"eval/{name}/{prec}", **obs)
     finally:
         ops.set_precision("bf16")
 
@@ -137,21 +231,21 @@ def test_public_submodule_api():
             gf, pf = m.encoder(x.cuda())
             gf_ref, pf_ref = wo.encoder_forward(sd, x)
             assert pf.shape == (2, 200, 512)
-            assert_close(pf, pf_ref, 2e-4, "point_features"); assert_close(gf, gf_ref, 2e-4, "global_features")
+            assert_close(pf, pf_ref, 2e-5, "point_features"); assert_close(gf, gf_ref, 2e-5, "global_features")
             vo = m.vertex_predictor(gf, pf, None)
             v_ref, p_ref, c_ref = wo.vertex_forward(sd, gf_ref, pf_ref, 10)
-            assert_close(vo["vertices"], v_ref, 2e-4, "vertices")
+            assert_close(vo["vertices"], v_ref, 2e-5, "vertices")
             assert torch.equal(vo["actual_vertex_counts"].cpu(), c_ref)
             probs, idx = m.edge_predictor(vo["vertices"][:, :6, :].contiguous())
             for b in range(2):
                 pr, pairs = wo.edge_forward(sd, v_ref[b, :6])
-                assert_close(probs[b], pr, 5e-4, "edge probs"); assert idx == pairs.tolist()
+                assert_close(probs[b], pr, 2e-5, "edge probs"); assert idx == pairs.tolist()
             with pytest.raises(IndexError):
                 m.edge_predictor(vo["vertices"][:, :1, :].contiguous())
         ops.set_precision("bf16")
         with torch.no_grad():
             gf2, pf2 = m.encoder(x.cuda())
-        assert_close(pf2, pf_ref, 5e-2, "bf16 point_features")
+        assert_close(pf2, pf_ref, 1e-2, "bf16 point_features")
     finally:
         ops.set_precision("bf16")
 
@@ -281,17 +375,27 @@ def test_real_building_vs_reference_golden(golden_dir, prec):
         pi, ti = crit._hungarian_matching(pred, tgt)[0]
         assert np.array_equal(pi, ref_match[0]) and np.array_equal(ti, ref_match[1])
         fails = []
+        from gpu_util import record
+        obs = {"vertices": rel_err(pred["vertices"], torch.from_numpy(g["vertices"])),
+               "edge_probs": rel_err(pred["edge_probs"], torch.from_numpy(g["edge_probs"])),
+               "global_features": rel_err(pred["global_features"], torch.from_numpy(g["global_features"])),
+               "loss_exist_edge": float(np.max(np.abs(got[2:] - g["losses"][2:]) / g["losses"][2:])),
+               "loss_total_vertex": float(np.max(np.abs(got[:2] - g["losses"][:2]) / g["losses"][:2])), "gnorm": {}}
         for k, p in m.named_parameters():
             if "gnone/" + k in g:
                 assert p.grad is None, k
                 continue
             ref_norm = float(g["gnorm/" + k][0])
             e = abs(float(p.grad.double().norm()) - ref_norm) / max(ref_norm, 1e-12)
+            obs["gnorm"][k] = round(e, 7)
             # raw intensity: the first LayerNorm's backward is ill-conditioned in fp32 (in the reference too); a different
             # (equally optimal within noise) matching changes the vertex-term gradients of the heads
             loose = 30.0 if k.startswith("encoder.mlp.0.") else (10.0 if prec == "fp32" else 1.0)
             if e > gtol * loose:
                 fails.append((k, e))
+        obs["gnorm_worst"] = max(obs["gnorm"].values()); obs["gnorm_worst_excl_l1"] = max(v for k, v in obs["gnorm"].items() if not k.startswith("encoder.mlp.0."))
+        del obs["gnorm"]
+        record(f"real_building/{prec}", **obs)
         assert not fails, f"{prec} gradient-norm mismatches: {fails[:6]}"
     finally:
         ops.set_precision("bf16")
@@ -376,9 +480,9 @@ def test_unusual_shapes_vs_oracle(B, N, V, max_count):
         ld = crit(pred, tg)
         ld["total_loss"].backward()
         crit.check_pending()
-        assert_close(pred["vertices"], pred_ref["vertices"], 2e-4, "vertices")
-        assert_close(pred["edge_probs"], pred_ref["edge_probs"], 5e-4, "edge_probs")
-        assert abs(ld["total_loss"].item() - ld_ref["total_loss"].item()) <= 2e-4 * abs(ld_ref["total_loss"].item())
+        assert_close(pred["vertices"], pred_ref["vertices"], 2e-5, "vertices")
+        assert_close(pred["edge_probs"], pred_ref["edge_probs"], 2e-5, "edge_probs")
+        assert abs(ld["total_loss"].item() - ld_ref["total_loss"].item()) <= 2e-5 * abs(ld_ref["total_loss"].item())
         ours = crit._hungarian_matching(pred, tg)
         # the oracle's matching of OUR predictions: cost matrices bit-equal, assignment index-identical
         ref = wo.loss_matching({k: pred[k].detach().cpu() for k in ("vertices", "existence_probabilities")}, tgt)
@@ -396,7 +500,7 @@ def test_unusual_shapes_vs_oracle(B, N, V, max_count):
             assert V >= 200, "matching flipped between oracle and GPU predictions on a small problem"
         for name in names:
             g = dict(model.named_parameters())[name].grad
-            assert_close(g, sdr[name].grad, 3e-3, name)
+            assert_close(g, sdr[name].grad, 2e-4, name)
     finally:
         ops.set_precision("bf16")
 
@@ -429,7 +533,7 @@ def test_fewer_input_features_use_the_tensor_core_encoder(input_dim):
     ops.set_precision("bf16")
     assert grads["bf16"]["mlp.0.weight"].shape == (512, input_dim)
     for a, b in zip(outs["bf16"], outs["fp32"]):
-        assert_close(a, b, 5e-2, "pooled features bf16 vs fp32 path")
+        assert_close(a, b, 1e-2, "pooled features bf16 vs fp32 path")
     for k in ("mlp.0.weight", "mlp.4.weight", "mlp.16.weight"):
         ga, gb = grads["bf16"][k].double(), grads["fp32"][k].double()
         assert float((ga - gb).norm() / gb.norm()) < 8e-2, k
@@ -437,9 +541,26 @@ def test_fewer_input_features_use_the_tensor_core_encoder(input_dim):
     sd = {f"encoder.{k}": v.detach().cpu() for k, v in enc.state_dict().items()}
     pf = wo.encoder_point_features(sd, x.cpu())
     ref_max = pf.max(dim=1).values
-    assert_close(outs["fp32"][2], ref_max, 2e-4, "unmasked max vs oracle")
+    assert_close(outs["fp32"][2], ref_max, 2e-5, "unmasked max vs oracle")
     # inference (chunked, no grad) takes the same route
     with torch.no_grad():
         ri = enc.pooled(x)
     for a, b in zip(ri[:4], outs["bf16"]):
         assert torch.equal(a, b) or rel_err(a, b) < 1e-6
+
+
+def test_hungarian_rmse_vs_reference_golden(golden_dir):
+    """models/utils.py:38-55 on wf_cdist_f64 + wf_lsap_f64: identical to the unmodified reference (fp64 cdist, fp64
+    assignment) on random, rectangular and heavily tied vertex sets; float32 inputs keep the reference's float32 final
+    expression; NaN input raises scipy's ValueError like the reference's linear_sum_assignment call."""
+    from models.utils import hungarian_rmse
+    g = dict(np.load(os.path.join(golden_dir, "hungarian_rmse.npz")))
+    for k, want in enumerate(g["rmse"]):
+        got = hungarian_rmse(g[f"p/{k}"], g[f"t/{k}"])
+        assert abs(float(got) - float(want)) <= 1e-12 * max(1.0, abs(float(want))), (k, got, want)
+        assert np.asarray(got).dtype == np.result_type(g[f"p/{k}"].dtype, g[f"t/{k}"].dtype)
+    assert hungarian_rmse(np.zeros((0, 3)), np.zeros((0, 3))) == 0.0
+    assert hungarian_rmse(np.zeros((0, 3)), np.ones((2, 3))) == float("inf")
+    bad = g["p/0"].copy(); bad[1, 2] = np.nan
+    with pytest.raises(ValueError, match="invalid numeric"):
+        hungarian_rmse(bad, g["t/0"])

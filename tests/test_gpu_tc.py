@@ -127,6 +127,9 @@ def test_encoder_tc_vs_fp32_path(ops):
             # 8e-2: the first layer's bias/gain gradients are sums with LayerNorm cancellation, the most noise-sensitive
             assert e < (8e-2 if not use_max else 2.5e-1), f"use_max={use_max} grad {k}: {e:.3e}"
         print(f"encoder bf16 vs fp32 (max pools in path: {use_max}): worst grad error {worst}, argmax agreement {agree:.4f}")
+        from gpu_util import record
+        record(f"encoder_tc_vs_fp32/use_max={use_max}", worst_param=worst[0], worst=worst[1], argmax_agreement=agree,
+               pooled=max(rel_err(a, b) for a, b in zip(res["bf16"][0][:4], res["fp32"][0][:4])))
 
 
 def test_enc_l1_kernels_fp32_dtype(ops):

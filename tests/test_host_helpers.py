@@ -49,3 +49,47 @@ def test_loss_overlap_rule():
     assert crit._overlap_events({"vertices": pv}, tagged) == ["EV_PRED", "EV_TGT", "EV_TGT"]
     half = {"vertices": tagged["vertices"], "vertex_counts": tgt["vertex_counts"].clone()}
     assert crit._overlap_events({"vertices": pv}, half) is None                       # one untagged, unseen target is enough
+
+
+def test_loss_overlap_rule_is_by_identity_not_by_address():
+    """fresh target tensors of the next batch are routinely handed the previous batch's recycled address with
+    version 0.  They must NOT be taken for "the tensors of the previous call"."""
+    from losses.WireframeLoss import WireframeLoss
+    crit = WireframeLoss()
+    pv = torch.zeros(2, 4, 3)
+    pv._wf_ready = "EV_PRED"
+    seen_addresses = set()
+    hits = 0
+    for step in range(6):
+        # a per-step function that builds its targets afresh: the allocator recycles the storage of the previous step's
+        tgt = {"vertices": torch.full((2, 4, 3), float(step)), "vertex_counts": torch.tensor([2 + step % 2, 3])}
+        seen_addresses.add((tgt["vertices"].data_ptr(), tgt["vertex_counts"].data_ptr()))
+        if crit._overlap_events({"vertices": pv}, tgt) is not None:
+            hits += 1
+        del tgt
+    assert hits == 0, "fresh untagged targets were mistaken for the previous call's tensors"
+    # (on this allocator the 6 batches typically produce 1-2 distinct address pairs: the aliasing scenario is the common case)
+
+
+def test_host_counts_never_keyed_on_an_address():
+    """PointCloudToWireframe._host_counts must return the counts of THE tensor it is given."""
+    from models.PointCloudToWireframe import PointCloudToWireframe
+    m = PointCloudToWireframe.__new__(PointCloudToWireframe)      # no parameters needed for the host helper
+    m._count_cache = None
+    for step in range(6):
+        vals = [2 + step, 3 + step, 4]
+        t = torch.tensor(vals)                                     # fresh tensor per batch, recycled address
+        assert m._host_counts(t) == vals
+        del t
+    assert m._host_counts([5, 6]) == [5, 6] and m._host_counts((7,)) == [7]
+    # the host tag set by wf_b200.targets is honoured only at the version it was made for
+    class FakeCuda(torch.Tensor):
+        is_cuda = True
+    t = torch.tensor([9, 9]).as_subclass(FakeCuda)
+    t._wf_host_counts = (t._version, (4, 5))
+    assert m._host_counts(t) == [4, 5]
+    t.add_(1)                                                      # modified after tagging: tag is stale, values are read
+    assert m._host_counts(t) == [10, 10]
+    assert m._host_counts(t) == [10, 10]                           # same object, same version: remembered
+    t.add_(1)
+    assert m._host_counts(t) == [11, 11]

@@ -81,9 +81,14 @@ class WireframeLoss(nn.Module):
             ev = getattr(t, '_wf_ready', None)
             if ev is not None:
                 waits.append(ev)
-            sig.append((t.data_ptr(), t._version, tuple(t.shape), ev is not None))
+            sig.append((t, t._version, ev is not None))
+        # "already used by the previous call" means THE SAME TENSOR OBJECTS at the same version.  The previous call's
+        # tensors are held here, so a new batch cannot be mistaken for them through a recycled address (fresh tensors
+        # copied on the main stream after the model forward would otherwise be read by the side stream mid-copy).
         seen, self._seen_targets = self._seen_targets, sig
-        if all(s[3] for s in sig) or seen == sig:
+        if all(s[2] for s in sig):
+            return waits
+        if seen is not None and all(a[0] is b[0] and a[1] == b[1] for a, b in zip(seen, sig)):
             return waits
         return None
 

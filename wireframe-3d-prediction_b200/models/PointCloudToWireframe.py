@@ -23,14 +23,27 @@ class PointCloudToWireframe(nn.Module):
         self._count_cache = None
 
     def _host_counts(self, t):
-        """One device->host read per distinct counts tensor (train.py passes the same tensor every step)."""
+        """Host copy of the ground-truth vertex counts.
+
+        * a list / tuple / CPU tensor is read directly;
+        * a device tensor that carries `_wf_host_counts` (wf_b200.targets.prepare_targets and DevicePrefetcher attach the
+          host values they packed the tensor from, together with the tensor's version at that moment) costs nothing;
+        * otherwise one device->host read -- remembered only for THE SAME TENSOR OBJECT at the same version (train.py
+          passes one tensor every step).  The tensor itself is held, so its address cannot be recycled for another
+          batch while the entry lives: identity is `is`, never an address (a fresh tensor of the next batch routinely
+          gets the previous one's address from the caching allocator with version 0)."""
         if not torch.is_tensor(t):
             return [int(c) for c in t]
-        key = (t.data_ptr(), t._version, tuple(t.shape), t.device)
-        if self._count_cache is not None and self._count_cache[0] == key:
-            return self._count_cache[1]
-        vals = [int(c) for c in t.tolist()]
-        self._count_cache = (key, vals)
+        if not t.is_cuda:
+            return [int(c) for c in t.tolist()]
+        tag = getattr(t, "_wf_host_counts", None)
+        if tag is not None and tag[0] == t._version:
+            return list(tag[1])
+        c = self._count_cache
+        if c is not None and c[0] is t and c[1] == t._version:
+            return c[2]
+        vals = [int(v) for v in t.tolist()]
+        self._count_cache = (t, t._version, vals)
         return vals
 
     def forward(self, point_cloud, target_vertex_counts=None):

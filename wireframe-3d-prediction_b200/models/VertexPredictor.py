@@ -37,8 +37,6 @@ class VertexPredictor(nn.Module):
 
     def forward_pooled(self, global_features, pooled_mean, pooled_max):
         """Same computation as forward(), fed with the already-reduced point features."""
-        if self.vertex_dim != 4:
-            raise NotImplementedError("vertex_dim != 4 is not built (reference default is 4)")
         batch_size = global_features.shape[0]
         if pooled_mean is not None:
             pooled = torch.cat([pooled_mean, pooled_max], dim=1)
@@ -54,6 +52,12 @@ class VertexPredictor(nn.Module):
         r2 = ops.linear_ln_act(eg, self.residual_proj2.weight, self.residual_proj2.bias)
         x = ops.linear_ln_act(x, m4[0].weight, m4[0].bias, m4[1].weight, m4[1].bias, ACT_RELU, residual=r2)
         vf = ops.linear_ln_act(x, self.final_layer.weight, self.final_layer.bias)
+        if self.vertex_dim != 4:
+            # the reference views (B, V, vertex_dim) and reads columns 0:3 and 3 (models/VertexPredictor.py:118-122): wider
+            # rows carry unused columns, narrower ones fail on the existence column with torch's IndexError
+            if self.vertex_dim < 4:
+                raise IndexError(f"index 3 is out of bounds for dimension 2 with size {self.vertex_dim}")
+            vf = vf.view(batch_size, self.max_vertices, self.vertex_dim)[:, :, :4].reshape(batch_size, self.max_vertices * 4)
         coords, prob, count = ops.VertexSplit.apply(vf, self.max_vertices)
         return {'vertices': coords, 'existence_probabilities': prob, 'actual_vertex_counts': count}
 

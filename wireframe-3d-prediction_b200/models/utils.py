@@ -25,18 +25,15 @@ def create_adjacency_matrix_from_predictions(edge_probs, edge_indices, num_verti
 
 
 def hungarian_rmse(pred_vertices, true_vertices):
-    """RMSE under the optimal L2 matching (reference models/utils.py:38-55); the assignment runs on the GPU."""
+    """RMSE under the optimal L2 matching (reference models/utils.py:38-55): fp64 pairwise distances and the fp64
+    assignment both run on the device (wf_cdist_f64 + wf_lsap_f64, the kernels of the evaluation post-processing), scipy's
+    ValueError for invalid entries is raised like the reference's linear_sum_assignment call would."""
     if len(pred_vertices) == 0 and len(true_vertices) == 0:
         return 0.0
     if len(pred_vertices) == 0 or len(true_vertices) == 0:
         return float('inf')
-    from wf_b200 import ops
-    p = torch.as_tensor(np.asarray(pred_vertices), dtype=torch.float64)
-    t = torch.as_tensor(np.asarray(true_vertices), dtype=torch.float64)
-    cost = torch.cdist(p, t).float().cuda().unsqueeze(0).contiguous()
-    nr = torch.tensor([p.shape[0]], dtype=torch.int32, device=cost.device)
-    nc = torch.tensor([t.shape[0]], dtype=torch.int32, device=cost.device)
-    col, _ = ops.lsap_batched(cost, nr, nc)
-    col = col[0].cpu()
-    rows = torch.nonzero(col >= 0).flatten()
-    return float(np.sqrt(np.mean((p[rows].numpy() - t[col[rows].long()].numpy()) ** 2)))
+    from wf_b200 import evalpost
+    pv, tv = np.asarray(pred_vertices), np.asarray(true_vertices)
+    # scipy's cdist works in float64 whatever the inputs are; the final expression keeps the inputs' own dtype (:52-55)
+    rows, cols, _ = evalpost.cdist_assign_batched([pv.astype(np.float64)], [tv.astype(np.float64)])[0]
+    return np.sqrt(np.mean((pv[rows] - tv[cols]) ** 2))

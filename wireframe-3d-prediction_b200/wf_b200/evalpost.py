@@ -105,9 +105,8 @@ def hausdorff_assign_batched(p_lines: Sequence[np.ndarray], t_lines: Sequence[np
     return _solve_device(out, o_off, shapes, dev)
 
 
-def cdist_batched(a_list: Sequence[np.ndarray], b_list: Sequence[np.ndarray]) -> List[np.ndarray]:
-    """scipy.spatial.distance.cdist(a, b) (euclidean, float64) for every pair of the two lists."""
-    dev = _device()
+def _cdist_device(a_list, b_list, dev):
+    """Pack, launch wf_cdist_f64; returns (device matrix buffer or None, block offsets, shapes)."""
     B = len(a_list)
     dim = 3
     for x in list(a_list) + list(b_list):
@@ -121,14 +120,34 @@ def cdist_batched(a_list: Sequence[np.ndarray], b_list: Sequence[np.ndarray]) ->
     o_off = _offsets([n * m for n, m in shapes])
     total = int(o_off[-1])
     if total == 0:
-        return [np.zeros(s) for s in shapes]
+        return None, o_off, shapes
     d_a, d_b = _dev(af, dev), _dev(bf, dev)
     d_ao, d_bo, d_oo = _dev(a_off, dev), _dev(b_off, dev), _dev(o_off, dev)
     out = torch.empty(total, dtype=torch.float64, device=dev)
     _lib.call("wf_cdist_f64", ops._p(d_a), ops._p(d_ao), ops._p(d_b), ops._p(d_bo), ops._p(d_oo), B,
               max(n * m for n, m in shapes), dim, ops._p(out), ops._s())
     ops._count()
+    return out, o_off, shapes
+
+
+def cdist_batched(a_list: Sequence[np.ndarray], b_list: Sequence[np.ndarray]) -> List[np.ndarray]:
+    """scipy.spatial.distance.cdist(a, b) (euclidean, float64) for every pair of the two lists."""
+    out, o_off, shapes = _cdist_device(a_list, b_list, _device())
+    if out is None:
+        return [np.zeros(s) for s in shapes]
     return _split_blocks(out.cpu().numpy(), o_off, shapes)
+
+
+def cdist_assign_batched(a_list: Sequence[np.ndarray], b_list: Sequence[np.ndarray]):
+    """models/utils.py:45-49 for every pair of the two lists: fp64 Euclidean cdist -> linear_sum_assignment, both on the
+    device (the matrices never leave it).  Returns [(row_ind, col_ind, matched distances)]; raises scipy's ValueError
+    texts for NaN / infeasible matrices."""
+    dev = _device()
+    out, o_off, shapes = _cdist_device(a_list, b_list, dev)
+    if out is None:
+        e = np.zeros(0, dtype=np.int64)
+        return [(e, e, np.zeros(0)) for _ in shapes]
+    return _solve_device(out, o_off, shapes, dev)
 
 
 def _solve_device(d_cost: torch.Tensor, c_off: np.ndarray, shapes, dev):

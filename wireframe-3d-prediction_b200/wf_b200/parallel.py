@@ -92,9 +92,11 @@ class GradAllReduce:
         self._stream = None
         self._built = False
         self._bucket_of: Dict[torch.nn.Parameter, dict] = {}
+        self._hooked = set()
         for p in module.parameters():
             if p.requires_grad:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+                self._hooked.add(id(p))
 
     # ---- step protocol: zero() -> forward/backward -> finish() -> optimizer.step()
     def zero(self) -> None:
@@ -119,6 +121,9 @@ class GradAllReduce:
         if b is None:
             return
         b["pending"] -= 1
+        if b["pending"] < 0:
+            raise RuntimeError("GradAllReduce: a parameter received a second gradient before finish(); the bucket it belongs to "
+                               "has already been handed to NCCL (one backward per zero()/finish() pair)")
         if b["pending"] == 0:
             self._launch([q.grad for q in b["params"] if q.grad is not None])
 
@@ -147,11 +152,23 @@ class GradAllReduce:
         else:
             self._reduce_list(tensors)
 
+    def _check_registered(self) -> None:
+        """Every parameter that received a gradient must have been seen at construction: a parameter created later (the
+        lazy vertex_predictor.point_pool_proj when the reducer is built before the first forward) would never
+        be reduced and the replicas would drift apart silently."""
+        hooked = self._hooked
+        late = [n for n, p in self.module.named_parameters() if p.requires_grad and p.grad is not None and id(p) not in hooked]
+        if late:
+            raise RuntimeError("GradAllReduce: parameters created after the reducer was built received gradients and would "
+                               f"not be all-reduced: {late}.  Run one forward (materialising lazy layers, with identical "
+                               "weights on every rank) before constructing GradAllReduce.")
+
     def finish(self) -> None:
-        """Call after backward().  First step: fixes the buckets from the observed gradient order and reduces everything
-        at once; later steps: waits for the in-flight bucket reductions."""
+        """Call after backward() -- ONE backward per zero()/finish() pair.  First step: fixes the buckets from the observed
+        gradient order and reduces everything at once; later steps: waits for the in-flight bucket reductions."""
         if self.world == 1:
             return
+        self._check_registered()
         if not self._built:
             self._build()
             self._launch([p.grad for b in self.buckets for p in b["params"]])

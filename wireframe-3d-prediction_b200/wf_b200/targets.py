@@ -54,6 +54,9 @@ def prepare_targets(wf_vertices: Sequence[torch.Tensor], wf_edges: Sequence[torc
     done.record()
     for t in out.values():
         ops.mark_ready(t, done)          # lets WireframeLoss start its matching on a side stream (see _match_device)
+    # the host already knows the counts it packed: PointCloudToWireframe.forward needs no device->host read for them
+    # (valid while the tensor is not modified: the tag carries the version it was made at)
+    out["vertex_counts"]._wf_host_counts = (out["vertex_counts"]._version, tuple(counts))
     return out
 
 
@@ -81,6 +84,8 @@ class DevicePrefetcher:
                 if torch.is_tensor(v):
                     src = v if v.is_pinned() else v.pin_memory()
                     dev_batch[k] = src.to(self.dev, non_blocking=True)
+                    if k == "vertex_counts":          # host values travel with the device copy (no read-back in the step)
+                        dev_batch[k]._wf_host_counts = (dev_batch[k]._version, tuple(int(c) for c in v.tolist()))
                 else:
                     dev_batch[k] = v
             ev = torch.cuda.Event()
