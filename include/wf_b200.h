@@ -223,6 +223,49 @@ int wf_seg_mean(const float* part, const float* valid, int B, int points_per_clo
 int wf_pool_finalize(const uint64_t* packed_u, const uint64_t* packed_m, const float* lin,
                      const float* bias, int B, int C, float* max_m, int32_t* arg_m, float* avg_m,
                      float* max_u, int32_t* arg_u, float* mean_u, wf_stream_t stream);
+
+/* Side jobs: HBM-bound row passes executed by 128 spare threads INSIDE the persistent tensor-core GEMM kernel.
+ * The wide GEMMs of the per-point MLP (models/PointNetEncoder.py:37-45) are bound by the tensor pipe and leave HBM almost
+ * idle; the LayerNorm+ReLU passes between them (:38-39, and their backward) are bound by HBM and leave the tensor pipe
+ * idle.  A GEMM launch on one row chunk therefore carries the LayerNorm pass of ANOTHER row chunk (already produced by an
+ * earlier launch): both finish in about the time of the longer one.  A segment is rows [0, rows) of its own tensors (the
+ * caller offsets the pointers); the rows of every segment are dealt across the CTAs of the launch.
+ *   WF_SIDE_LN_FWD         h = relu(LN(z))                         == wf_ln_relu_bf16_fwd         (bit-identical)
+ *   WF_SIDE_LN_FWD_COLSUM  ... + per-row-block column sums of h    == wf_ln_relu_bf16_fwd_colsum  (bit-identical)
+ *   WF_SIDE_LN_BWD         dz from dh and z, dgamma/dbeta/dbias    == wf_ln_relu_bf16_bwd         (same math; the row sums are
+ *                          accumulated atomically                     added in a different order: ~1e-7 relative before rounding)
+ * C in {1024, 2048}; up to WF_SIDE_MAX segments per launch, executed in order. */
+#define WF_SIDE_LN_FWD 1
+#define WF_SIDE_LN_FWD_COLSUM 2
+#define WF_SIDE_LN_BWD 3
+#define WF_SIDE_MAX 4
+typedef struct wf_side_seg {
+    int32_t kind;            /* WF_SIDE_* */
+    int32_t C;               /* row width (channels) */
+    int64_t rows;            /* rows of this segment */
+    const void* x0;          /* fwd: z [rows, C] bf16            bwd: dh [rows, C] bf16 */
+    const void* x1;          /* fwd: unused                      bwd: z  [rows, C] bf16 */
+    const float* mean;       /* [rows] */
+    const float* rstd;       /* [rows] */
+    const float* gamma;      /* [C] */
+    const float* beta;       /* [C] */
+    void* out;               /* fwd: h [rows, C] bf16            bwd: dz [rows, C] bf16 */
+    float* acc0;             /* bwd: dgamma [C] (accumulated) */
+    float* acc1;             /* bwd: dbeta  [C] (accumulated) */
+    float* acc2;             /* bwd: dbias  [C] (accumulated) */
+    const uint8_t* mask;     /* colsum: [rows] validity, or NULL */
+    float* part;             /* colsum: the whole `part` buffer (indexed by global row block) */
+    int32_t pool_n;          /* colsum: points per cloud */
+    int32_t row_off;         /* colsum: global row index of the segment's row 0 (multiple of 128) */
+} wf_side_seg;
+
+/* wf_gemm_bf16 / wf_gemm_bf16_pool (pool_n > 0: the pooling epilogue, D unused) carrying side-job segments.  Needs the
+ * 2-SM kernel form (M >= 256 rows); the GEMM results are bit-identical to the plain entry points. */
+int wf_gemm_bf16_side(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M,
+                      int N, int K, const float* bias, void* D, int ldd, int out_dtype, int accumulate,
+                      int split_k, float* rowstats, int pool_n, int pool_row_offset, int pool_index_offset,
+                      const uint8_t* pool_mask, uint64_t* pool_max_u, uint64_t* pool_max_m,
+                      const wf_side_seg* segs, int n_segs, wf_stream_t stream);
 /* Backward of the four pools THROUGH the final Linear (W [C,K] fp32, h [B*N,K] bf16 its input) without dense GEMMs:
  * the pooled gradients are per-cloud constants plus <= 2C single entries at the argmax rows (train.py:140 autograd
  * reaches the same numbers through a dense (B*N,C) gradient).  dbar[2][B][K] = [g_mean_u; g_avg_m] W (caller).

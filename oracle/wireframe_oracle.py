@@ -156,13 +156,35 @@ def _ln(sd, name, x):
     return F.layer_norm(x, (w.shape[0],), w, sd[name + ".bias"], 1e-5)
 
 
-def encoder_point_features(sd, x: torch.Tensor) -> torch.Tensor:
-    """models/PointNetEncoder.py:30-48,90-98 -- the per-point MLP (Linear+LN+ReLU x4, Linear)."""
+def _q(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 (nearest even) in the forward value, identity in the backward (straight-through)."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def encoder_point_features(sd, x: torch.Tensor, emulate_bf16: bool = False, return_hidden: bool = False):
+    """models/PointNetEncoder.py:30-48,90-98 -- the per-point MLP (Linear+LN+ReLU x4, Linear).
+
+    emulate_bf16: the SAME function with the roundings of the product's bf16 mode inserted where its kernels round
+    (DESIGN.md 2.3): post-ReLU activations h1..h4 and the weights of layers 2-5 are rounded to bf16 before each product,
+    the pre-LayerNorm z2..z4 are rounded to bf16 AFTER their row statistics were taken from the unrounded fp32 values,
+    accumulation stays fp32.  Gradients are straight-through.  With it the oracle predicts the bf16 mode's outputs to
+    ~1e-5 instead of ~3e-3, so ReLU masks, argmax and matchings coincide and gradients can be compared tightly."""
     B, N, D = x.shape
     h = x.reshape(B * N, D)
-    for li in range(4):
-        h = torch.relu(_ln(sd, f"encoder.mlp.{4 * li + 1}", _lin(sd, f"encoder.mlp.{4 * li}", h)))
-    return _lin(sd, "encoder.mlp.16", h).reshape(B, N, -1)
+    if not emulate_bf16:
+        for li in range(4):
+            h = torch.relu(_ln(sd, f"encoder.mlp.{4 * li + 1}", _lin(sd, f"encoder.mlp.{4 * li}", h)))
+        pf = _lin(sd, "encoder.mlp.16", h).reshape(B, N, -1)
+        return (pf, h) if return_hidden else pf
+    h = _q(torch.relu(_ln(sd, "encoder.mlp.1", _lin(sd, "encoder.mlp.0", h))))          # layer 1: fp32 math, bf16 store
+    for li in range(1, 4):
+        z = F.linear(h, _q(sd[f"encoder.mlp.{4 * li}.weight"]), sd[f"encoder.mlp.{4 * li}.bias"])
+        mean = z.mean(dim=1, keepdim=True)
+        rstd = torch.rsqrt(z.var(dim=1, unbiased=False, keepdim=True) + 1e-5)
+        y = (_q(z) - mean) * rstd * sd[f"encoder.mlp.{4 * li + 1}.weight"] + sd[f"encoder.mlp.{4 * li + 1}.bias"]
+        h = _q(torch.relu(y))
+    pf = F.linear(h, _q(sd["encoder.mlp.16.weight"]), sd["encoder.mlp.16.bias"]).reshape(B, N, -1)
+    return (pf, h) if return_hidden else pf
 
 
 def encoder_pools(x: torch.Tensor, pf: torch.Tensor):
@@ -175,20 +197,34 @@ def encoder_pools(x: torch.Tensor, pf: torch.Tensor):
     return mask, avg, mx, arg
 
 
-def encoder_forward(sd, x):
-    """models/PointNetEncoder.py:67-119 -> (global_features[B,512], point_features[B,N,512])."""
-    pf = encoder_point_features(sd, x)
-    _, avg, mx, _ = encoder_pools(x, pf)
+def encoder_forward(sd, x, emulate_bf16: bool = False):
+    """models/PointNetEncoder.py:67-119 -> (global_features[B,512], point_features[B,N,512]).
+    emulate_bf16: see encoder_point_features; the mean pool is taken through the affine map like the product does
+    (mean of the bf16 h4, then the fp32 master weight of the final Linear -- DESIGN.md 2.2)."""
+    if not emulate_bf16:
+        pf = encoder_point_features(sd, x)
+        _, avg, mx, _ = encoder_pools(x, pf)
+    else:
+        pf, h4 = encoder_point_features(sd, x, True, return_hidden=True)
+        mask, _, mx, _ = encoder_pools(x, pf)
+        B, N = x.shape[:2]
+        cnt = mask.sum(dim=1, keepdim=True).clamp(min=1).to(pf.dtype)
+        hbar = (h4.reshape(B, N, -1) * mask.unsqueeze(-1)).sum(dim=1) / cnt
+        avg = _lin(sd, "encoder.mlp.16", hbar)
     g = torch.cat([mx, avg], dim=1)
     g = torch.relu(_ln(sd, "encoder.feature_fusion.1", _lin(sd, "encoder.feature_fusion.0", g)))
     g = torch.relu(_ln(sd, "encoder.feature_fusion.4", _lin(sd, "encoder.feature_fusion.3", g)))
-    return _lin(sd, "encoder.feature_fusion.6", g), pf
+    gf = _lin(sd, "encoder.feature_fusion.6", g)
+    if emulate_bf16:
+        mean_u = _lin(sd, "encoder.mlp.16", h4.reshape(B, N, -1).mean(dim=1))
+        return gf, pf, mean_u
+    return gf, pf
 
 
-def vertex_forward(sd, gfeat, pf, max_vertices: int):
+def vertex_forward(sd, gfeat, pf, max_vertices: int, mean_override=None):
     """models/VertexPredictor.py:63-133 (unmasked mean/max pool, projection, 4 LN-MLP blocks with
     two residuals added AFTER LN+ReLU, final layer, sigmoid, >0.5 count)."""
-    pooled = torch.cat([pf.mean(dim=1), pf.max(dim=1).values], dim=1)
+    pooled = torch.cat([pf.mean(dim=1) if mean_override is None else mean_override, pf.max(dim=1).values], dim=1)
     eg = gfeat + _lin(sd, "vertex_predictor.point_pool_proj", pooled)
     blk = lambda k, t: torch.relu(_ln(sd, f"vertex_predictor.vertex_mlp{k}.1",
                                       _lin(sd, f"vertex_predictor.vertex_mlp{k}.0", t)))
@@ -235,12 +271,16 @@ def edge_forward(sd, verts: torch.Tensor):
     return torch.sigmoid(_lin(sd, "edge_predictor.edge_mlp.10", e)).reshape(-1), pairs
 
 
-def model_forward(sd, x, target_counts=None, *, training: bool, max_vertices: int):
+def model_forward(sd, x, target_counts=None, *, training: bool, max_vertices: int, emulate_bf16: bool = False):
     """models/PointCloudToWireframe.py:43-121.  Edge head runs per sample on the PREFIX
     vertices[:count] (GT count when training, #(p>0.5) otherwise -- SURVEY Q5), results are
     zero-padded to the batch maximum edge count."""
-    gfeat, pf = encoder_forward(sd, x)
-    verts, prob, dyn = vertex_forward(sd, gfeat, pf, max_vertices)
+    if emulate_bf16:
+        gfeat, pf, mean_u = encoder_forward(sd, x, True)
+        verts, prob, dyn = vertex_forward(sd, gfeat, pf, max_vertices, mean_override=mean_u)
+    else:
+        gfeat, pf = encoder_forward(sd, x)
+        verts, prob, dyn = vertex_forward(sd, gfeat, pf, max_vertices)
     B = x.shape[0]
     use = target_counts if (training and target_counts is not None) else dyn
     probs, idx = [], []
@@ -420,12 +460,13 @@ def detr_matcher(outputs, targets: Sequence[dict], cost_class=1.0, cost_bbox=1.0
 # one full training step on the oracle (used by bench.py's cpu_baseline leg)
 # --------------------------------------------------------------------------------------
 def train_step(sd_params: Dict[str, torch.Tensor], x, targets, *, max_vertices: int,
-               weights=(3.0, 1.0, 1.5)):
+               weights=(3.0, 1.0, 1.5), emulate_bf16: bool = False, matches=None):
     """fwd + loss + bwd as train.py:127-140 does (weights from train.py:90-94).
-    sd_params must hold leaf tensors with requires_grad=True.  Returns the loss dict."""
+    sd_params must hold leaf tensors with requires_grad=True.  Returns the loss dict.
+    emulate_bf16: the product's bf16-mode roundings inserted (encoder_point_features); matches: a fixed assignment."""
     pred = model_forward(sd_params, x, targets["vertex_counts"], training=True,
-                         max_vertices=max_vertices)
+                         max_vertices=max_vertices, emulate_bf16=emulate_bf16)
     ld = loss_forward(pred, targets, vertex_weight=weights[0], edge_weight=weights[1],
-                      existence_weight=weights[2])
+                      existence_weight=weights[2], matches=matches)
     ld["total_loss"].backward()
     return ld, pred

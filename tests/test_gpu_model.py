@@ -38,9 +38,16 @@ def _model(seed, V, train):
 # written by gpu_util.record) and the fp32 gradient ones cannot go below the reference's OWN reproducibility: two runs of the
 # unmodified reference on this container's 8 threads differ by up to 1.4e-5 on a gradient entry and 1e-5 on a gradient norm
 # (MKL summation order; measured while regenerating the fixtures).
+# bf16 mode against the fp32 REFERENCE: outputs 1e-2 (observed 5e-3).  Its gradients are compared by norm (3e-2, observed
+# 2.4e-2) and by the direction of the whole gradient (cosine >= 0.99): entry by entry they differ from the fp32 reference by
+# up to ~0.4 of the largest entry EVEN THOUGH every kernel is exact to rounding, because a forward perturbation of 3e-3 flips
+# the ReLU mask of the few units that sit within 3e-3 of zero, and at batch size 2 a head's weight-gradient row is a sum over
+# TWO samples (tools/diag_bf16_grads.py: same level with the reference's matching AND argmax injected, TF32 heads on or off;
+# fp32 mode: 2e-6).  The entry-by-entry check of the bf16 mode is therefore made against the oracle evaluated WITH the bf16
+# mode's roundings inserted (test_bf16_mode_vs_bf16_emulating_oracle below), where masks, argmax and matching coincide.
 TOL = {
-    "fp32": dict(out=2e-5, loss=2e-5, gnorm=5e-5, gelem=2e-4, dx=2e-4),
-    "bf16": dict(out=1e-2, loss=5e-3, gnorm=3e-2, gelem=5e-2, dx=None),
+    "fp32": dict(out=2e-5, loss=2e-5, gnorm=5e-5, gelem=2e-4, dx=2e-4, cost=1e-5),
+    "bf16": dict(out=1e-2, loss=5e-3, gnorm=3e-2, gelem=None, dx=None, cost=5e-3, cosine=0.99),
 }
 
 
@@ -52,15 +59,47 @@ def _ref_col(g, B, V):
     return col
 
 
+def _assignment_cost(cost_b, pi, ti, count):
+    """Total cost of a filtered assignment on one sample's (V, V) loss cost matrix: matched real columns + the constant
+    dummy-column cost of every unmatched prediction row (losses/WireframeLoss.py:216-219)."""
+    V = cost_b.shape[0]
+    tot = float(cost_b[pi, ti].double().sum())
+    un = np.setdiff1d(np.arange(V), pi)
+    if len(un) and count < V:
+        tot += float(cost_b[un, count].double().sum())
+    return tot
+
+
+def _check_own_matching(crit, pred, tg, g, B, tol_cost):
+    """Our assignment equals the reference's, or -- where near-tied costs make the optimum itself ill-defined -- has the
+    same total cost on OUR cost matrix to within rounding.  Returns the number of samples with identical pairs."""
+    from wf_b200 import ops
+    ours = crit._hungarian_matching(pred, tg)
+    _, _, cost = ops.loss_match(pred["vertices"], pred["existence_probabilities"], tg["vertices"], tg["vertex_counts"],
+                                want_cost=True)
+    cost = cost.cpu()
+    same = 0
+    for b, (pi, ti) in enumerate(ours):
+        rp, rt = g[f"match_p/{b}"], g[f"match_t/{b}"]
+        if np.array_equal(pi, rp) and np.array_equal(ti, rt):
+            same += 1
+            continue
+        cnt = int(tg["vertex_counts"][b])
+        c_own, c_ref = _assignment_cost(cost[b], pi, ti, cnt), _assignment_cost(cost[b], rp, rt, cnt)
+        assert c_own <= c_ref * (1 + 1e-6) + 1e-6, f"sample {b}: our assignment costs more than the reference's on our own matrix"
+        assert c_ref - c_own <= tol_cost * abs(c_ref), f"sample {b}: assignments differ and are not tied ({c_own} vs {c_ref})"
+    return same
+
+
 @pytest.mark.parametrize("name", TRAIN)
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_train_step_vs_reference_golden(golden_dir, name, prec):
     """One training step through the drop-in modules against the UNMODIFIED reference's outputs, losses, matching, argmax and
     all 80 parameter gradients (norm + 16 leading + <=1024 strided entries each) -- incl. BASELINE.json's real shape
     (2 clouds x 10,000 points, 64 vertex slots, counts ~ U{16..64}).
-    fp32 mode: matchings, counts identical; argmax identical wherever the reference's top-2 gap exceeds 1e-5*|max|.
-    bf16 mode: gradients are compared ELEMENT-WISE with the reference's matching injected, so a flipped assignment (a
-    legitimate discontinuity under bf16-sized perturbations) cannot hide an error; the flip rate itself is recorded."""
+    Matching: identical pairs, or an assignment of equal cost (to rounding) where the reference's optimum is tied; the loss
+    and the gradients are then taken with the REFERENCE's assignment injected, so that a flipped assignment cannot hide (or
+    fake) a gradient error.  Argmax (fp32): identical wherever the reference's top-2 gap exceeds 1e-5*|max|."""
     from oracle import wireframe_oracle as wo
     from wf_b200 import ops
     from losses.WireframeLoss import WireframeLoss
@@ -79,14 +118,9 @@ def test_train_step_vs_reference_golden(golden_dir, name, prec):
         tg = {k: v.cuda() for k, v in tgt.items()}
         pred = m(xg, counts.cuda())
         crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)
-        ours = crit._hungarian_matching(pred, tg)
-        same_pairs = sum(int(np.array_equal(pi, g[f"match_p/{b}"]) and np.array_equal(ti, g[f"match_t/{b}"]))
-                         for b, (pi, ti) in enumerate(ours))
-        if prec == "fp32":
-            assert same_pairs == B, "fp32 matching differs from the reference's"
-        else:
-            ref_col = _ref_col(g, B, V).cuda()
-            crit._match_device = lambda predictions, targets, sync=None: ref_col      # the reference's assignment, injected
+        same_pairs = _check_own_matching(crit, pred, tg, g, B, tol["cost"])
+        ref_col = _ref_col(g, B, V).cuda()
+        crit._match_device = lambda predictions, targets, sync=None: ref_col          # the reference's assignment, injected
         ld = crit(pred, tg)
         ld["total_loss"].backward()
         obs = {"matching_identical_samples": same_pairs, "samples": B}
@@ -98,11 +132,13 @@ def test_train_step_vs_reference_golden(golden_dir, name, prec):
         assert [len(e) for e in pred["edge_indices"]] == g["n_edges"].tolist()
         got = np.array([ld[k].item() for k in ("total_loss", "vertex_loss", "existence_loss", "edge_loss")])
         obs["loss"] = float(np.max(np.abs(got - g["losses"]) / np.abs(g["losses"])))
-        np.testing.assert_allclose(got, g["losses"], rtol=tol["loss"], atol=0)
+        # raw intensity (~5e4): the bf16 rounding of the first layer's output is amplified by its ill-conditioned LayerNorm
+        np.testing.assert_allclose(got, g["losses"], rtol=tol["loss"] * (4 if rawint and prec == "bf16" else 1), atol=0)
         if prec == "fp32":
             assert np.array_equal(pred["actual_vertex_counts"].cpu().numpy(), g["dyn_counts"])
         worst_n, worst_e = ("", 0.0), ("", 0.0)
         fails = []
+        dot = n_our = n_ref = 0.0
         for k, p in m.named_parameters():
             if "gnone/" + k in g:
                 assert p.grad is None, k
@@ -115,17 +151,23 @@ def test_train_step_vs_reference_golden(golden_dir, name, prec):
             # element-wise on the strided sample; the scale is the parameter's RMS gradient entry or the sample's largest
             scale = max(float(samp.abs().max()), ref_norm / np.sqrt(gr.numel()))
             es = float((gr[::stride] - samp).abs().max()) / scale
+            l1 = k.startswith("encoder.mlp.0.") or k.startswith("encoder.mlp.1.")
+            if not (rawint and l1):
+                dot += float(gr[::stride] @ samp) * stride; n_our += float(gr[::stride].norm() ** 2) * stride; n_ref += float(samp.norm() ** 2) * stride
             if e > worst_n[1]:
                 worst_n = (k, e)
             if es > worst_e[1]:
                 worst_e = (k, es)
             # un-normalised intensity (~5e4) makes the first layer's LayerNorm backward ill-conditioned
             # in fp32 (rstd ~ 1e-4, heavy cancellation): the reference's own fp32 gradient is only ~1e-2 accurate there
-            loose = (600.0 if k.startswith("encoder.mlp.0.") else 20.0) if (rawint and prec == "fp32") else 1.0
-            if e > tol["gnorm"] * loose or es > tol["gelem"] * loose:
+            loose = (600.0 if l1 else 20.0) if (rawint and prec == "fp32") else (4.0 if rawint and l1 else 1.0)
+            if e > tol["gnorm"] * loose or (tol["gelem"] is not None and es > tol["gelem"] * loose):
                 fails.append((k, f"norm {e:.2e}", f"elem {es:.2e}"))
         obs["grad_norm_worst"], obs["grad_norm_worst_param"] = worst_n[1], worst_n[0]
         obs["grad_elem_worst"], obs["grad_elem_worst_param"] = worst_e[1], worst_e[0]
+        obs["grad_cosine_sampled"] = dot / max(1e-300, np.sqrt(n_our * n_ref))
+        if prec == "bf16":
+            assert obs["grad_cosine_sampled"] >= tol["cosine"], f"gradient direction: cosine {obs['grad_cosine_sampled']:.4f}"
         # d/d(input) is a 512-term sum with LayerNorm cancellation: not meaningful under bf16 noise, nor in fp32 with
         # un-normalised intensity (the reference's own fp32 value is noise-dominated there)
         if prec == "fp32" and not rawint:
@@ -149,6 +191,147 @@ def test_train_step_vs_reference_golden(golden_dir, name, prec):
         print(prec, name, obs)
         assert not fails, f"{prec} gradient mismatches: {fails[:6]} (+{max(0, len(fails) - 6)} more)"
     finally:
+        ops.set_precision("bf16")
+
+
+@pytest.mark.parametrize("B,N,V,cmin,cmax,seed", [(2, 384, 12, 2, 12, 3), (4, 1500, 32, 8, 32, 41), (2, 10000, 64, 16, 64, 23)])
+def test_bf16_mode_vs_bf16_emulating_oracle(B, N, V, cmin, cmax, seed):
+    """The production (bf16) mode entry by entry.  The oracle is evaluated WITH the bf16 mode's roundings inserted where the
+    kernels round (oracle.encoder_point_features(emulate_bf16=True): bf16 h1..h4 / z2..z4 / weights of layers 2-5, fp32
+    statistics and accumulation, mean pools through the affine map; straight-through gradients).  It then predicts the bf16
+    mode's forward to ~1e-5 -- ReLU masks, argmax and matching coincide -- and what remains in the gradients is the bf16
+    rounding of the stored gradient tensors (dz, dh: 2^-9 per stage), which is smooth.  The heads' products run in fp32
+    here (the TF32 tensor-core path is compared with the fp32 path in tests/test_gpu_tc.py); the assignment and the argmax
+    indices of the oracle are injected, so that the comparison cannot be spoilt by a tie."""
+    from oracle import wireframe_oracle as wo
+    from wf_b200 import ops
+    from losses.WireframeLoss import WireframeLoss
+    from gpu_util import record
+    # The oracle's roundings and the kernels' cannot coincide exactly: the fp32 values that get rounded differ by ~1e-6
+    # (summation order), which moves ~5e-4 of them across a bf16 rounding boundary -> a residual of ~8 % of the plain bf16
+    # noise: outputs agree to ~3e-4 instead of ~3e-3 (asserted: 2e-3).
+    OUT_EMU = 2e-3
+    ops.set_precision("bf16")
+    tf32 = ops.USE_TF32_HEADS
+    ops.USE_TF32_HEADS = False
+    try:
+        m = _model(seed, V, True)
+        x, tgt, counts = wo.make_inputs(seed, B, N, V, norm_intensity=True, min_count=cmin, max_count=cmax)
+        sd = wo.make_state_dict(seed, V)
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        pred_o = wo.model_forward(sdr, x, counts, training=True, max_vertices=V, emulate_bf16=True)
+        matches = wo.loss_matching(pred_o, tgt)
+        ld_o = wo.loss_forward(pred_o, tgt, 3.0, 1.0, 1.5, matches=matches)
+        ld_o["total_loss"].backward()
+        with torch.no_grad():
+            pf = wo.encoder_point_features(sd, x, True)
+            _, _, _, arg_m = wo.encoder_pools(x, pf)
+            arg_u = pf.max(dim=1).indices
+        col = torch.full((B, V), -1, dtype=torch.int32)
+        for b, (pi, ti) in enumerate(matches):
+            col[b, torch.as_tensor(pi)] = torch.as_tensor(ti).to(torch.int32)
+        col = col.cuda()
+        ops.ARGMAX_OVERRIDE = (arg_m.to(torch.int32).cuda(), arg_u.to(torch.int32).cuda())
+        pred = m(x.cuda(), counts.cuda())
+        ops.ARGMAX_OVERRIDE = None
+        crit = WireframeLoss(vertex_weight=3.0, edge_weight=1.0, existence_weight=1.5)
+        own = crit._hungarian_matching(pred, {k: v.cuda() for k, v in tgt.items()})
+        same = sum(int(np.array_equal(a, c) and np.array_equal(b_, d)) for (a, b_), (c, d) in zip(own, matches))
+        crit._match_device = lambda predictions, targets, sync=None: col
+        ld = crit(pred, {k: v.cuda() for k, v in tgt.items()})
+        ld["total_loss"].backward()
+        r = m.encoder.pooled(x.cuda())
+        obs = {"matching_identical_samples": same, "samples": B,
+               "argmax_agreement": float((r[5].cpu() == arg_u).float().mean()),
+               "vertices": assert_close(pred["vertices"], pred_o["vertices"], OUT_EMU, "vertices"),
+               "existence": assert_close(pred["existence_probabilities"], pred_o["existence_probabilities"], OUT_EMU, "existence"),
+               "edge_probs": assert_close(pred["edge_probs"], pred_o["edge_probs"], OUT_EMU, "edge_probs"),
+               "global_features": assert_close(pred["global_features"], pred_o["global_features"], OUT_EMU, "global_features"),
+               "loss": abs(ld["total_loss"].item() - ld_o["total_loss"].item()) / abs(ld_o["total_loss"].item())}
+        assert obs["loss"] < 5e-4
+        worst_f, worst_e, fails = ("", 0.0), ("", 0.0), []
+        dot = n_a = n_b = 0.0
+        for k, p in m.named_parameters():
+            go = sdr[k].grad
+            if go is None or float(go.abs().max()) == 0.0:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+                continue
+            a, b_ = p.grad.detach().double().cpu().reshape(-1), go.double().reshape(-1)
+            fro = float((a - b_).norm() / b_.norm())
+            scale = max(float(b_.abs().max()), float(b_.norm()) / np.sqrt(b_.numel()))
+            el = float((a - b_).abs().max()) / scale
+            if fro > worst_f[1]:
+                worst_f = (k, fro)
+            if el > worst_e[1]:
+                worst_e = (k, el)
+            dot += float(a @ b_); n_a += float(a @ a); n_b += float(b_ @ b_)
+            # Frobenius-relative per parameter: observed <= 3.6e-2 (heads: the few ReLU units that still flip at batch 2-4;
+            # encoder: inherits the pooled gradient's error uniformly).  A single flipped unit moves single entries of a
+            # head's bias gradient by up to 0.3 of the largest entry, so entries are not asserted one by one here -- the
+            # encoder's backward is (test_bf16_encoder_backward_vs_bf16_emulating_oracle).
+            if fro > 1e-1:
+                fails.append((k, f"fro {fro:.2e}", f"elem {el:.2e}"))
+        obs.update(grad_fro_worst=worst_f[1], grad_fro_worst_param=worst_f[0], grad_elem_worst=worst_e[1],
+                   grad_elem_worst_param=worst_e[0], grad_cosine=dot / np.sqrt(n_a * n_b))
+        assert obs["grad_cosine"] >= 0.999, f"direction of the whole gradient: cosine {obs['grad_cosine']:.5f}"
+        record(f"bf16_emulating_oracle/B{B}_N{N}_V{V}", **obs)
+        print(obs)
+        assert not fails, f"bf16-mode gradients vs the bf16-emulating oracle: {fails[:6]} (+{max(0, len(fails) - 6)} more)"
+    finally:
+        ops.USE_TF32_HEADS = tf32
+        ops.ARGMAX_OVERRIDE = None
+        ops.set_precision("bf16")
+
+
+@pytest.mark.parametrize("B,N", [(2, 700), (3, 4000)])
+def test_bf16_encoder_backward_vs_bf16_emulating_oracle(B, N):
+    """The tensor-core encoder's backward ENTRY BY ENTRY: all 18 parameter gradients of the per-point MLP for fixed upstream
+    gradients on the four pooled outputs, against autograd through the bf16-emulating oracle (same roundings in the
+    forward, straight-through), with the oracle's argmax injected.  No head in the path: what remains is the bf16 storage of
+    dz / dh and the few ReLU units within ~3e-4 of zero, averaged over thousands of points."""
+    from oracle import wireframe_oracle as wo
+    from models.PointNetEncoder import PointNetEncoder
+    from wf_b200 import ops
+    from gpu_util import record
+    ops.set_precision("bf16")
+    try:
+        torch.manual_seed(0)
+        enc = PointNetEncoder().cuda()
+        sd = {k: v for k, v in wo.make_state_dict(21, 16).items() if k.startswith("encoder.")}
+        enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items()})
+        x, _, _ = wo.make_inputs(7, B, N, 16, pad_frac=0.1, norm_intensity=True)
+        gen = torch.Generator().manual_seed(1)
+        gs = [torch.randn(B, 512, generator=gen) for _ in range(4)]
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        pf, h4 = wo.encoder_point_features(sdr, x, True, return_hidden=True)
+        mask, _, mx_m, arg_m = wo.encoder_pools(x, pf)
+        cnt = mask.sum(dim=1, keepdim=True).clamp(min=1).float()
+        h3 = h4.reshape(B, N, -1)
+        avg_m = torch.nn.functional.linear((h3 * mask.unsqueeze(-1)).sum(1) / cnt, sdr["encoder.mlp.16.weight"], sdr["encoder.mlp.16.bias"])
+        mean_u = torch.nn.functional.linear(h3.mean(1), sdr["encoder.mlp.16.weight"], sdr["encoder.mlp.16.bias"])
+        mx_u, arg_u = pf.max(dim=1)
+        (mx_m * gs[0] + avg_m * gs[1] + mx_u * gs[2] + mean_u * gs[3]).sum().backward()
+        ops.ARGMAX_OVERRIDE = (arg_m.to(torch.int32).cuda(), arg_u.to(torch.int32).cuda())
+        r = enc.pooled(x.cuda())
+        ops.ARGMAX_OVERRIDE = None
+        sum(t * g_.cuda() for t, g_ in zip(r[:4], gs)).sum().backward()
+        obs = {"pooled": max(rel_err(a, b_) for a, b_ in zip(r[:4], (mx_m, avg_m, mx_u, mean_u))),
+               "argmax_agreement": float((r[5].cpu() == arg_u).float().mean())}
+        assert obs["pooled"] < 2e-3
+        worst_f, worst_e = ("", 0.0), ("", 0.0)
+        for k, p in enc.named_parameters():
+            if not k.startswith("mlp."):
+                continue
+            a, b_ = p.grad.double().cpu().reshape(-1), sdr["encoder." + k].grad.double().reshape(-1)
+            fro = float((a - b_).norm() / b_.norm())
+            el = float((a - b_).abs().max()) / max(float(b_.abs().max()), float(b_.norm()) / np.sqrt(b_.numel()))
+            worst_f = max(worst_f, (k, fro), key=lambda t: t[1]); worst_e = max(worst_e, (k, el), key=lambda t: t[1])
+        obs.update(grad_fro_worst=worst_f[1], grad_fro_worst_param=worst_f[0], grad_elem_worst=worst_e[1], grad_elem_worst_param=worst_e[0])
+        record(f"bf16_encoder_bwd_vs_emulating_oracle/B{B}_N{N}", **obs)
+        print(obs)
+        assert worst_f[1] < 3e-2 and worst_e[1] < 6e-2, obs
+    finally:
+        ops.ARGMAX_OVERRIDE = None
         ops.set_precision("bf16")
 
 

@@ -1,0 +1,76 @@
+"""CPU: the side-job planner (wf_b200/sidesched.py) -- every LayerNorm item is dealt exactly once, inside its window
+(after the launch that produces its input, before the launch that consumes its output), in row-block aligned segments,
+at most WF_SIDE_MAX per launch; items without a window fall back to stand-alone passes."""
+import random
+
+from wf_b200 import sidesched as ss
+
+
+def _check(durs, items, side, pre):
+    n = len(durs)
+    cover = {id(it): [] for it in items}
+    by_key = {it.key: it for it in items}
+    for j, segs in enumerate(side):
+        assert len(segs) <= ss.SIDE_MAX
+        for key, r0, r1 in segs:
+            it = by_key[key]
+            assert it.avail < j < it.deadline, (key, j, it.avail, it.deadline)
+            cover[id(it)].append((r0, r1))
+    for j, segs in pre.items():
+        for key, r0, r1 in segs:
+            it = by_key[key]
+            assert j == it.deadline
+            cover[id(it)].append((r0, r1))
+    for it in items:
+        segs = sorted(cover[id(it)])
+        assert segs and segs[0][0] == it.r0 and segs[-1][1] == it.r1, (it.key, segs)
+        for (a0, a1), (b0, b1) in zip(segs, segs[1:]):
+            assert a1 == b0                                   # contiguous, no overlap
+        for r0, r1 in segs:
+            assert r1 > r0 and (r0 - it.r0) % ss.ROW_ALIGN == 0
+
+
+def test_split_rows():
+    assert ss.split_rows(640000, 2) == [(0, 320000), (320000, 640000)]
+    ch = ss.split_rows(640000, 3)
+    assert ch[0][0] == 0 and ch[-1][1] == 640000 and all(a % 256 == 0 for a, _ in ch) and all(b == c for (_, b), (c, _) in zip(ch, ch[1:]))
+    assert ss.split_rows(100, 4) == [(0, 100)]
+    assert ss.split_rows(513, 2) == [(0, 512), (512, 513)]
+
+
+def test_forward_plan_of_the_encoder():
+    # layer-major forward over 2 chunks: G[li][c] for three layers, then the pooling GEMM per chunk
+    chunks = ss.split_rows(640000, 2)
+    flops = [2 * 512 * 1024, 2 * 1024 * 2048, 2 * 2048 * 1024, 2 * 1024 * 512]
+    widths = [1024, 2048, 1024]
+    idx = {}
+    durs = []
+    for li in range(4):
+        for c, (r0, r1) in enumerate(chunks):
+            idx[(li, c)] = len(durs)
+            durs.append((r1 - r0) * flops[li] / 1.3e15)
+    items = [ss.Item((li, c), r0, r1, widths[li] * 4, idx[(li, c)], idx[(li + 1, c)]) for li in range(3) for c, (r0, r1) in enumerate(chunks)]
+    side, pre = ss.plan(durs, items, 2.0e12)
+    _check(durs, items, side, pre)
+    assert not pre                                             # every item has a window
+    assert not side[0]                                         # nothing exists yet under the first launch
+
+
+def test_items_without_a_window_run_stand_alone_and_random_plans_are_valid():
+    durs = [1e-3] * 4
+    items = [ss.Item("a", 0, 1000, 4096, -1, 0), ss.Item("b", 0, 777, 4096, 0, 1), ss.Item("c", 256, 5000, 8192, 0, 4)]
+    side, pre = ss.plan(durs, items, 2.0e12)
+    _check(durs, items, side, pre)
+    assert pre[0] == [("a", 0, 1000)] and pre[1] == [("b", 0, 777)]
+    rnd = random.Random(0)
+    for trial in range(200):
+        n = rnd.randint(1, 12)
+        durs = [rnd.uniform(1e-4, 2e-3) for _ in range(n)]
+        items = []
+        for k in range(rnd.randint(1, 8)):
+            a = rnd.randint(-1, n - 1)
+            d = rnd.randint(a + 1, n)
+            r0 = 256 * rnd.randint(0, 50)
+            items.append(ss.Item(k, r0, r0 + rnd.randint(1, 400000), rnd.choice([4096, 8192, 6144, 12288]), a, d))
+        side, pre = ss.plan(durs, items, rnd.choice([5e11, 2e12, 1e13]))
+        _check(durs, items, side, pre)

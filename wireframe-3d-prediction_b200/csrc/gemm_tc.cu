@@ -20,6 +20,7 @@
 //   LayerNorm, then bf16 store, fp32 store or fp32 atomic accumulate (split-K).
 #include "wf_common.cuh"
 #include "sm100_ptx.cuh"
+#include "ln_side.cuh"
 
 #include <cuda.h>
 #include <mutex>
@@ -49,6 +50,9 @@ constexpr int BIAS_BYTES = EPI_WARPS * 32 * 4;                // per epilogue wa
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + BIAS_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
+constexpr int MAXST = 6;                                      // most pipeline stages of any kernel form (barrier slots)
+constexpr int SIDE_THREADS = 128;                             // SIDE kernels: warps 12..15 run the side-job segments
+constexpr int SIDE_BAR = 1;                                   // named barrier of the side warps (0 = __syncthreads)
 static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA)");
 
 // staging tile addressing: element (row r, column c) of a 32x32 fp32 tile; 16-byte groups are XOR-swizzled with the row so
@@ -74,6 +78,10 @@ struct Params {
     const uint8_t* pool_mask;
     unsigned long long* pool_max_u;
     unsigned long long* pool_max_m;
+    // SIDE kernels: pipeline stages actually used (the ring's unused tail, (6 - n_stages) * 32 KB, is the side warps' shared
+    // memory) and the side-job segments (include/wf_b200.h, wf_side_seg)
+    int n_stages, n_side;
+    wf_side_seg side[WF_SIDE_MAX];
 };
 
 // float -> uint32 whose unsigned order is the float order (-inf < ... < -0 < +0 < ... < +inf)
@@ -127,6 +135,43 @@ struct Sched {
     }
 };
 
+// ---- side jobs (warps 12..15 of a SIDE kernel): HBM-bound LayerNorm passes of another row chunk, see ln_side.cuh -------------
+template <int C8, bool COLSUM>
+__device__ __forceinline__ void side_ln_fwd(const wf_side_seg& sg, int tid, int worker, int n_workers, uint8_t* smem) {
+    const lnb::FwdArgs a{static_cast<const uint4*>(sg.x0), sg.mean, sg.rstd, sg.gamma, sg.beta, static_cast<uint4*>(sg.out),
+                         sg.mask, (int)sg.rows, COLSUM ? sg.pool_n : 1, COLSUM ? sg.row_off : 0, sg.part};
+    const int nblk = (int)((sg.rows + lnb::CS_R - 1) / lnb::CS_R);
+    for (int vb = worker; vb < nblk; vb += n_workers)
+        lnb::ln_fwd_block<C8, COLSUM, SIDE_THREADS>(a, vb, tid, reinterpret_cast<float*>(smem), SIDE_BAR);
+}
+template <int C8, int RG, int NSTG, bool GB_SMEM>
+__device__ __forceinline__ void side_ln_bwd(const wf_side_seg& sg, int tid, int worker, int n_workers, uint8_t* smem) {
+    const lnb::BwdArgs a{static_cast<const uint4*>(sg.x0), static_cast<const uint4*>(sg.x1), sg.mean, sg.rstd, sg.gamma, sg.beta,
+                         static_cast<uint4*>(sg.out), sg.acc0, sg.acc1, sg.acc2, (long long)sg.rows};
+    lnb::ln_bwd_side<C8, SIDE_THREADS, RG, NSTG, GB_SMEM>(a, worker, n_workers, tid, smem, SIDE_BAR);
+}
+// shared memory a segment needs (host side: picks n_stages)
+constexpr int SIDE_SMEM_FWD_COLSUM_1024 = 2 * 2 * 1024 * 4;
+constexpr int SIDE_SMEM_BWD_1024 = lnb::ln_bwd_side_smem<128, SIDE_THREADS, 2, 3, false>();
+constexpr int SIDE_SMEM_BWD_2048 = lnb::ln_bwd_side_smem<256, SIDE_THREADS, 2, 2, true>();
+static_assert(SIDE_SMEM_FWD_COLSUM_1024 <= 32768 && SIDE_SMEM_BWD_1024 <= 32768 && SIDE_SMEM_BWD_2048 <= 65536, "side smem");
+
+__device__ __forceinline__ void run_side_jobs(const Params& p, int tid, uint8_t* smem) {
+    const int worker = blockIdx.x, n_workers = gridDim.x;
+    for (int s = 0; s < p.n_side; ++s) {
+        const wf_side_seg& sg = p.side[s];
+        if (sg.kind == WF_SIDE_LN_FWD) {
+            if (sg.C == 1024) side_ln_fwd<128, false>(sg, tid, worker, n_workers, smem);
+            else side_ln_fwd<256, false>(sg, tid, worker, n_workers, smem);
+        } else if (sg.kind == WF_SIDE_LN_FWD_COLSUM) {
+            side_ln_fwd<128, true>(sg, tid, worker, n_workers, smem);
+        } else if (sg.kind == WF_SIDE_LN_BWD) {
+            if (sg.C == 1024) side_ln_bwd<128, 2, 3, false>(sg, tid, worker, n_workers, smem);
+            else side_ln_bwd<256, 2, 2, true>(sg, tid, worker, n_workers, smem);
+        }
+    }
+}
+
 // MODE 0: one CTA per tile.  MODE 1: clusters of 2, cta_group::1 MMAs, B tile multicast (see MC above).
 // MODE 2: clusters of 2 running ONE tcgen05.mma.cta_group::2 per k-step over a 256 x 256 tile: each CTA stages its own 128
 //         rows of A and only HALF of the B tile (128 of the 256 N rows), so a k-block costs 32 KB instead of 48 KB of
@@ -134,15 +179,21 @@ struct Sched {
 //         (TMA writes + MMA operand reads ~188 B/clk of 128), the 2-SM form is not.  The leader CTA (rank 0) issues the
 //         MMAs and owns the full/tmem-empty barriers; both CTAs' TMA bytes are credited to the leader's barrier; commits
 //         are multicast so each CTA's producer and epilogue see their own barriers flip.  Six 32 KB stages.
-template <int ESZ, bool A_KM, bool B_KM, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// SIDE (MODE 2 only): 128 more threads (warps 12..15) execute the side-job segments of p.side while the other roles run the
+//         GEMM; the ring uses p.n_stages (4 or 5) of its 6 slots and the rest is the side warps' shared memory; registers are
+//         re-dealt with setmaxnreg (512 threads x 128 at launch: producer/MMA warpgroup down to 56, the two epilogue
+//         warpgroups up to 160, the side warpgroup 136).
+template <int ESZ, bool A_KM, bool B_KM, int MODE, bool SIDE>
+__global__ void __launch_bounds__(NTHREADS + (SIDE ? SIDE_THREADS : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_d, const Params p) {
+               const __grid_constant__ CUtensorMap map_d, const __grid_constant__ Params p) {
     constexpr bool MC = MODE == 1, TWO = MODE == 2, CL = MODE != 0;
-    constexpr int NST = TWO ? 6 : STAGES;         // pipeline stages
+    static_assert(!SIDE || TWO, "side jobs ride on the 2-SM kernel form");
+    constexpr int NST_FULL = TWO ? 6 : STAGES;    // pipeline stages of the plain kernel forms
     constexpr int BB = TWO ? B_BYTES / 2 : B_BYTES;
-    constexpr int SB = A_BYTES + BB;              // bytes per stage (NST * SB == STAGES * STAGE_BYTES)
-    static_assert(NST * SB == STAGES * STAGE_BYTES, "ring size");
+    constexpr int SB = A_BYTES + BB;              // bytes per stage (NST_FULL * SB == STAGES * STAGE_BYTES)
+    static_assert(NST_FULL * SB == STAGES * STAGE_BYTES && NST_FULL <= MAXST, "ring size");
+    const int NST = SIDE ? p.n_stages : NST_FULL;
     constexpr int BK = 128 / ESZ;                 // elements of K per k-block
     constexpr int MNBOX = 128 / ESZ;              // MN-major: rows of the operand per TMA box (128 bytes)
     constexpr int BOX_BYTES = 128 * BK;           // MN-major box: BK k-rows x 128 bytes
@@ -151,10 +202,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NST + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NST + 2 + s); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * NST + 4));   // inside BAR_BYTES
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAXST + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAXST + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAXST + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * MAXST + 4));   // inside BAR_BYTES
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work items: clusters -> one item per CLUSTER covers two adjacent M tiles (this CTA takes 2*pair + rank)
@@ -182,9 +233,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (CL) ptx::cluster_sync();                 // peer barriers are initialised before any multicast / remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
+    // SIDE: the register file is re-dealt between the roles (whole warpgroups; 512 x 128 registers were allocated at launch).
+    // Each role executes its own setmaxnreg at the top of its branch, so that the branch's code is compiled for that budget.
+    if (SIDE && warp >= 12) {
+        // ------------------------------------------------------------------ side jobs
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+        run_side_jobs(p, (int)threadIdx.x - NTHREADS, smem + NST * SB);
+    } else if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
+        if (SIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             Sched sched(p, m_units, w_first, w_step);
@@ -250,6 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
+        if (SIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0 && (!TWO || crank == 0)) {
             constexpr uint32_t idesc = ptx::idesc_f32acc(ESZ == 2 ? 1 : 2, TWO ? 2 * BM : BM, BN, A_KM ? 0 : 1, B_KM ? 0 : 1);
             // one tcgen05.mma consumes 32 bytes of K per row: K-major advances 32 B inside the swizzle row,
@@ -290,8 +348,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        if (SIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");     // TMEM-allocator and spare warp: same warpgroup
+    } else if (warp < 12) {
         // ------------------------------------------------------------------ epilogue
+        if (SIDE) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
         // TMEM -> registers (thread = row): + bias, row statistics.  Then through a per-warp 32x32 fp32 staging tile in
         // shared memory so that global stores are row-contiguous (a quarter warp writes one 128-byte fp32 row segment /
         // a 64-byte bf16 segment) instead of 32 rows x 16 bytes per instruction.
@@ -580,29 +641,29 @@ static int make_store_map(CUtensorMap* m, void* ptr, uint64_t inner, uint64_t ou
 
 namespace wf { namespace tc {
 
-template <int ESZ, bool A_KM, bool B_KM, int MC>
+template <int ESZ, bool A_KM, bool B_KM, int MC, bool SIDE>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const Params& p, int grid, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<ESZ, A_KM, B_KM, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<ESZ, A_KM, B_KM, MC, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     WF_CUDA(attr_err);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS + (SIDE ? SIDE_THREADS : 0)); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = MC != 0 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    WF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<ESZ, A_KM, B_KM, MC>, ma, mb, md, p));
+    WF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<ESZ, A_KM, B_KM, MC, SIDE>, ma, mb, md, p));
     return WF_OK;
 }
 
 template <int ESZ, bool A_KM, bool B_KM>
 static int launch_mc(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const Params& p, int grid, cudaStream_t s) {
-    if (mode == 2) return launch<ESZ, A_KM, B_KM, 2>(ma, mb, md, p, grid, s);
-    if (mode == 1) return launch<ESZ, A_KM, B_KM, 1>(ma, mb, md, p, grid, s);
-    return launch<ESZ, A_KM, B_KM, 0>(ma, mb, md, p, grid, s);
+    if (mode == 2) return launch<ESZ, A_KM, B_KM, 2, false>(ma, mb, md, p, grid, s);
+    if (mode == 1) return launch<ESZ, A_KM, B_KM, 1, false>(ma, mb, md, p, grid, s);
+    return launch<ESZ, A_KM, B_KM, 0, false>(ma, mb, md, p, grid, s);
 }
 
 // WF_B200_GEMM_MODE: 2 (default) = 2-SM MMA, 1 = 1-SM MMA with multicast B, 0 = no clusters
@@ -617,7 +678,8 @@ struct PoolArgs { int n, row0, idx0; const uint8_t* mask; unsigned long long* ma
 // esz 2: bf16 operands; esz 4: fp32 operands multiplied as tf32
 static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N, int K,
                    const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k, float* rowstats,
-                   cudaStream_t stream, const PoolArgs* pool = nullptr, float* det_work = nullptr, long long det_work_floats = 0) {
+                   cudaStream_t stream, const PoolArgs* pool = nullptr, float* det_work = nullptr, long long det_work_floats = 0,
+                   const wf_side_seg* segs = nullptr, int n_segs = 0) {
     const int al = 16 / esz;                                     // elements per 16 bytes
     WF_CHECK_ARG(M > 0 && N > 0 && K > 0, "wf_gemm_tc: empty problem M=%d N=%d K=%d", M, N, K);
     WF_CHECK_ARG(lda % al == 0 && ldb % al == 0, "wf_gemm_tc: lda/ldb must be multiples of %d elements (16-byte TMA strides)", al);
@@ -638,6 +700,11 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     // multicast pairs pay off when there are at least two M tiles to pair up
     const int mode = (cdiv(M, BM) >= 2 && sm_count() >= 2) ? cluster_mode() : 0;
     const bool mc = mode != 0;
+    if (n_segs > 0) {
+        WF_CHECK_ARG(mode == 2 && esz == 2 && a_kmajor == b_kmajor, "wf_gemm_bf16_side: side jobs need the 2-SM bf16 kernel form "
+                     "(M >= 256, WF_B200_GEMM_MODE=2, both operands K-major or both MN-major)");
+        WF_CHECK_ARG(segs != nullptr && n_segs <= WF_SIDE_MAX, "wf_gemm_bf16_side: at most %d segments", WF_SIDE_MAX);
+    }
     if (b_kmajor) { if ((rc = make_map(&mb, esz, false, B, K, N, ldb, BKe, mc ? BN / 2 : BN)) != WF_OK) return rc; }
     else          { if ((rc = make_map(&mb, esz, true, B, N, K, ldb, mnbox, BKe)) != WF_OK) return rc; }
     Params p;
@@ -688,11 +755,41 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     p.tma_store = (tma_store_env && out_dtype == WF_BF16 && !p.accumulate && pool == nullptr && p.split_stride == 0) ? 1 : 0;
     CUtensorMap md = ma;                                         // placeholder when unused
     if (p.tma_store && (rc = make_store_map(&md, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd)) != WF_OK) return rc;
+    p.n_stages = 6; p.n_side = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        const wf_side_seg& sg = segs[i];
+        if (sg.rows <= 0) continue;
+        const bool fwd = sg.kind == WF_SIDE_LN_FWD || sg.kind == WF_SIDE_LN_FWD_COLSUM;
+        WF_CHECK_ARG(fwd || sg.kind == WF_SIDE_LN_BWD, "wf_gemm_bf16_side: segment %d: unknown kind %d", i, sg.kind);
+        WF_CHECK_ARG(sg.kind == WF_SIDE_LN_FWD_COLSUM ? sg.C == 1024 : (sg.C == 1024 || sg.C == 2048),
+                     "wf_gemm_bf16_side: segment %d: C=%d not built", i, sg.C);
+        WF_CHECK_ARG(sg.rows < (1ll << 31), "wf_gemm_bf16_side: segment %d: too many rows", i);
+        WF_CHECK_ARG(sg.x0 && sg.mean && sg.rstd && sg.gamma && sg.beta && sg.out && (fwd || (sg.x1 && sg.acc0 && sg.acc1 && sg.acc2)),
+                     "wf_gemm_bf16_side: segment %d: null pointer", i);
+        WF_CHECK_ARG(((reinterpret_cast<uintptr_t>(sg.x0) | reinterpret_cast<uintptr_t>(sg.x1) | reinterpret_cast<uintptr_t>(sg.out) |
+                       reinterpret_cast<uintptr_t>(sg.gamma) | reinterpret_cast<uintptr_t>(sg.beta)) & 15) == 0,
+                     "wf_gemm_bf16_side: segment %d: 16-byte alignment required", i);
+        if (sg.kind == WF_SIDE_LN_FWD_COLSUM)
+            WF_CHECK_ARG(sg.part && sg.pool_n >= lnb::CS_R && sg.row_off >= 0 && sg.row_off % lnb::CS_R == 0,
+                         "wf_gemm_bf16_side: segment %d: colsum needs part, points_per_cloud >= %d, row_off %% %d == 0", i, lnb::CS_R, lnb::CS_R);
+        const int need = fwd ? (sg.kind == WF_SIDE_LN_FWD_COLSUM ? SIDE_SMEM_FWD_COLSUM_1024 : 0)
+                             : (sg.C == 1024 ? SIDE_SMEM_BWD_1024 : SIDE_SMEM_BWD_2048);
+        const int st = need > 32768 ? 4 : 5;
+        if (st < p.n_stages) p.n_stages = st;
+        p.side[p.n_side++] = sg;
+    }
+    if (p.n_side > 0 && p.n_stages == 6) p.n_stages = 5;
     long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
                                 : (long long)m_units * p.tiles_n * p.split_k;
     const int workers = (int)(items < workers_max ? items : workers_max);
     const int grid = mc ? 2 * workers : workers;
     const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
+    if (p.n_side > 0) {
+        // every CTA of the launch takes its share of the side rows: always the full grid, whatever the GEMM's item count
+        const int sgrid = 2 * workers_max;
+        rc = a_kmajor ? launch<2, true, true, 2, true>(ma, mb, md, p, sgrid, stream) : launch<2, false, false, 2, true>(ma, mb, md, p, sgrid, stream);
+        if (rc != WF_OK || !det) return rc;
+    } else
     switch (key) {
         case 3: rc = launch_mc<2, true, true>(mode, ma, mb, md, p, grid, stream); break;
         case 2: rc = launch_mc<2, true, false>(mode, ma, mb, md, p, grid, stream); break;
@@ -732,6 +829,24 @@ extern "C" int wf_gemm_bf16_pool(const void* A, int lda, const void* B, int ldb,
     wf::tc::PoolArgs pa{points_per_cloud, row_offset, index_offset, mask, reinterpret_cast<unsigned long long*>(max_u),
                         reinterpret_cast<unsigned long long*>(max_m)};
     return wf::tc::gemm_tc(2, A, lda, 1, B, ldb, 1, M, N, K, bias, nullptr, 8, WF_BF16, 0, 1, nullptr, wf::as_stream(stream), &pa);
+}
+
+extern "C" int wf_gemm_bf16_side(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N, int K,
+                                 const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k, float* rowstats,
+                                 int pool_n, int pool_row_offset, int pool_index_offset, const uint8_t* pool_mask,
+                                 uint64_t* pool_max_u, uint64_t* pool_max_m, const wf_side_seg* segs, int n_segs,
+                                 wf_stream_t stream) {
+    WF_CHECK_ARG(n_segs >= 0 && (n_segs == 0 || segs != nullptr), "wf_gemm_bf16_side: bad segment list");
+    if (pool_n > 0) {
+        WF_CHECK_ARG(pool_n >= 32 && pool_row_offset >= 0 && pool_index_offset >= 0 && pool_max_u && pool_max_m && a_kmajor && b_kmajor,
+                     "wf_gemm_bf16_side: pooling epilogue needs points_per_cloud >= 32, packed outputs and K-major operands");
+        wf::tc::PoolArgs pa{pool_n, pool_row_offset, pool_index_offset, pool_mask, reinterpret_cast<unsigned long long*>(pool_max_u),
+                            reinterpret_cast<unsigned long long*>(pool_max_m)};
+        return wf::tc::gemm_tc(2, A, lda, 1, B, ldb, 1, M, N, K, bias, nullptr, 8, WF_BF16, 0, 1, nullptr, wf::as_stream(stream), &pa,
+                               nullptr, 0, segs, n_segs);
+    }
+    return wf::tc::gemm_tc(2, A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias, D, ldd, out_dtype, accumulate, split_k, rowstats,
+                           wf::as_stream(stream), nullptr, nullptr, 0, segs, n_segs);
 }
 
 extern "C" int wf_gemm_tf32(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, int M, int N,

@@ -15,124 +15,20 @@
 // every thread copies exactly the bytes it will consume, so the only wait is its own cp.async group -- no register
 // double buffering and three row groups of loads in flight per CTA.
 #include "wf_common.cuh"
+#include "ln_side.cuh"
 
 #include <mutex>
 
 namespace wf {
 namespace lnb {
 
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void up2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-// two bf16 in one 32-bit word -> (float(lo), float(hi))
-__device__ __forceinline__ u64 bf2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
-__device__ __forceinline__ uint32_t to_bf2(u64 v) {
-    float lo, hi;
-    up2(v, lo, hi);
-    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&t);
-}
-__device__ __forceinline__ u64 relu2(u64 v) { float lo, hi; up2(v, lo, hi); return pk2(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
-
-__device__ __forceinline__ void load_pairs(const float* p, u64 (&f)[4]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    f[0] = pk2(a.x, a.y); f[1] = pk2(a.z, a.w); f[2] = pk2(b.x, b.y); f[3] = pk2(b.z, b.w);
-}
-
-// h = relu(LN(z)) for one uint4 (8 channels) of a row with statistics (mu, rs)
-__device__ __forceinline__ uint4 ln_relu8(const uint4& u, float mu, float rs, const u64 (&gm)[4], const u64 (&bt)[4]) {
-    const u64 rs2 = pk2(rs, rs), nm2 = pk2(-mu * rs, -mu * rs);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = to_bf2(relu2(fma2(fma2(bf2(w[i]), rs2, nm2), gm[i], bt[i])));
-    return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
-// ------------------------------------------------------------------------------------------
-// forward.  A CTA (256 threads) owns CS_R consecutive rows; thread = (channel group c8, row phase rsub); four rows'
-// loads are issued before the first is used.  COLSUM (the LAST LayerNorm of the per-point MLP): also per-cloud column
-// sums of the output h (all rows / rows with mask != 0).  The final Linear is affine, so the two mean pools of its
-// output (models/PointNetEncoder.py:103-105, models/VertexPredictor.py:86) are that Linear applied to the mean of h:
-// the (B,N,512) point-feature tensor never has to exist for them.  Deterministic: partial sums go to
-// part[row block][segment][kind][C] (segment 1 = rows of the next cloud when the block straddles a cloud boundary) and are
-// added in block order by seg_mean_kernel.
-// ------------------------------------------------------------------------------------------
-constexpr int CS_R = 128;
-
+// forward, stand-alone: a CTA of 256 threads per block of CS_R rows (the body lives in ln_side.cuh, shared with the side-job
+// form inside the GEMM kernel)
 template <int C8, bool COLSUM>
 __global__ void __launch_bounds__(256)
-ln_relu_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, uint4* __restrict__ h,
-                   const uint8_t* __restrict__ mask, int M, int pool_n, int row_off, float* __restrict__ part) {
-    constexpr int C = C8 * 8, RS = 256 / C8, UN = 4;
-    __shared__ float red[COLSUM ? RS : 1][2][COLSUM ? C : 1];
-    const int tid = threadIdx.x, c8 = tid % C8, rsub = tid / C8;
-    const int blk_row0 = blockIdx.x * CS_R;
-    const int rows = min(CS_R, M - blk_row0);
-    const int g0 = row_off + blk_row0;                       // global row of this block's first row
-    const int rb = COLSUM ? (g0 / pool_n + 1) * pool_n - g0 : rows;   // local rows >= rb belong to the next cloud
-    const size_t gblk = (size_t)(g0 / CS_R);
-    u64 gm[4], bt[4];
-    load_pairs(gamma + c8 * 8, gm); load_pairs(beta + c8 * 8, bt);
-#pragma unroll 1
-    for (int seg = 0; seg < 2; ++seg) {
-        const int r_lo = seg == 0 ? 0 : rb, r_hi = seg == 0 ? min(rb, rows) : rows;
-        if (r_lo >= r_hi) break;                             // block-uniform
-        u64 su[4], sm[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) su[i] = sm[i] = 0ull;
-        for (int r = r_lo + rsub; r < r_hi; r += UN * RS) {
-            uint4 u[UN];
-            float mu[UN], rs[UN];
-            bool mk[UN];
-#pragma unroll
-            for (int j = 0; j < UN; ++j) {
-                const int rr = r + j * RS;
-                mk[j] = false; mu[j] = 0.f; rs[j] = 0.f; u[j] = make_uint4(0, 0, 0, 0);
-                if (rr < r_hi) {
-                    const size_t row = (size_t)blk_row0 + rr;
-                    u[j] = z[row * C8 + c8]; mu[j] = mean[row]; rs[j] = rstd[row];
-                    mk[j] = COLSUM && (mask == nullptr || mask[row] != 0);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < UN; ++j) {
-                const int rr = r + j * RS;
-                if (rr < r_hi) {
-                    const uint4 o = ln_relu8(u[j], mu[j], rs[j], gm, bt);
-                    h[((size_t)blk_row0 + rr) * C8 + c8] = o;
-                    if (COLSUM) {                            // sum what the next GEMM will read (bf16-rounded)
-                        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { const u64 v = bf2(w[i]); su[i] = add2(su[i], v); if (mk[j]) sm[i] = add2(sm[i], v); }
-                    }
-                }
-            }
-        }
-        if (COLSUM) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float lo, hi;
-                up2(su[i], lo, hi); red[rsub][0][c8 * 8 + 2 * i] = lo; red[rsub][0][c8 * 8 + 2 * i + 1] = hi;
-                up2(sm[i], lo, hi); red[rsub][1][c8 * 8 + 2 * i] = lo; red[rsub][1][c8 * 8 + 2 * i + 1] = hi;
-            }
-            __syncthreads();
-            float* dst = part + ((gblk * 2 + seg) * 2) * C;
-            for (int i = tid; i < 2 * C; i += 256) {
-                const int kind = i / C, c = i - kind * C;
-                float t = 0.f;
-#pragma unroll
-                for (int q = 0; q < RS; ++q) t += red[q][kind][c];
-                dst[(size_t)kind * C + c] = t;
-            }
-            __syncthreads();
-        }
-    }
+ln_relu_fwd_kernel(const FwdArgs a) {
+    __shared__ float red[COLSUM ? (256 / C8) * 2 * C8 * 8 : 1];
+    ln_fwd_block<C8, COLSUM, 256>(a, blockIdx.x, threadIdx.x, red, 0);
 }
 
 // hbar[kind][b][c] = (sum over the row blocks of cloud b, in order) * (kind 0: 1/N, kind 1: 1/valid[b])
@@ -153,12 +49,6 @@ __global__ void seg_mean_kernel(const float* __restrict__ part, const float* __r
 // backward.  CTA = C/8 threads (NW warps), rows in groups of RG, STAGES groups in flight through cp.async.
 // ------------------------------------------------------------------------------------------
 constexpr int RG = 4, STAGES = 3;
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW <= 4 ? 4 : 2)
@@ -333,7 +223,8 @@ extern "C" int wf_ln_relu_bf16_fwd(const void* z, const float* mean, const float
                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "wf_ln_relu_bf16_fwd: 16-byte alignment required");
     const int grid = cdiv(M, lnb::CS_R);
     cudaStream_t s = as_stream(stream);
-#define WF_LNF(C8) lnb::ln_relu_fwd_kernel<C8, false><<<grid, 256, 0, s>>>(static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(h), nullptr, M, 1, 0, nullptr)
+    const lnb::FwdArgs a{static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(h), nullptr, M, 1, 0, nullptr};
+#define WF_LNF(C8) lnb::ln_relu_fwd_kernel<C8, false><<<grid, 256, 0, s>>>(a)
     if (C == 512) WF_LNF(64); else if (C == 1024) WF_LNF(128); else WF_LNF(256);
 #undef WF_LNF
     WF_LAUNCH_CHECK();
@@ -352,7 +243,8 @@ extern "C" int wf_ln_relu_bf16_fwd_colsum(const void* z, const float* mean, cons
                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "wf_ln_relu_bf16_fwd_colsum: 16-byte alignment required");
     const int grid = cdiv(M, lnb::CS_R);
     cudaStream_t s = as_stream(stream);
-#define WF_LNC(C8) lnb::ln_relu_fwd_kernel<C8, true><<<grid, 256, 0, s>>>(static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(h), mask, M, points_per_cloud, row_offset, part)
+    const lnb::FwdArgs a{static_cast<const uint4*>(z), mean, rstd, gamma, beta, static_cast<uint4*>(h), mask, M, points_per_cloud, row_offset, part};
+#define WF_LNC(C8) lnb::ln_relu_fwd_kernel<C8, true><<<grid, 256, 0, s>>>(a)
     if (C == 512) WF_LNC(64); else if (C == 1024) WF_LNC(128); else WF_LNC(256);
 #undef WF_LNC
     WF_LAUNCH_CHECK();

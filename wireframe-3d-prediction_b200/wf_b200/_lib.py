@@ -41,6 +41,7 @@ SIGNATURES = {
     "wf_gemm_bf16": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, I, P, P],
     "wf_gemm_tf32": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, P],
     "wf_gemm_tf32_splitk": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, P, L, P],
+    "wf_gemm_bf16_side": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, I, P, I, I, I, P, P, P, P, I, P],
     "wf_ln_relu_bf16_fwd": [P, P, P, P, P, P, I, I, P],
     "wf_ln_relu_bf16_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
     "wf_stats_finalize": [P, I, I, I, F, P, P, P],
@@ -71,6 +72,17 @@ SIGNATURES = {
     "wf_loss_fwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, F, F, F, P, P],
     "wf_loss_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, F, F, P, P, P, P],
 }
+SIDE_LN_FWD, SIDE_LN_FWD_COLSUM, SIDE_LN_BWD, SIDE_MAX = 1, 2, 3, 4
+
+
+class SideSeg(ctypes.Structure):
+    """include/wf_b200.h: wf_side_seg -- one side-job segment of wf_gemm_bf16_side."""
+    _fields_ = [("kind", ctypes.c_int32), ("C", ctypes.c_int32), ("rows", ctypes.c_int64),
+                ("x0", c_void_p), ("x1", c_void_p), ("mean", c_void_p), ("rstd", c_void_p), ("gamma", c_void_p),
+                ("beta", c_void_p), ("out", c_void_p), ("acc0", c_void_p), ("acc1", c_void_p), ("acc2", c_void_p),
+                ("mask", c_void_p), ("part", c_void_p), ("pool_n", ctypes.c_int32), ("row_off", ctypes.c_int32)]
+
+
 _RESTYPE = {"wf_last_error": ctypes.c_char_p}
 _NO_STATUS = {"wf_version", "wf_last_error", "wf_loss_out_floats", "wf_seg_part_floats", "wf_pool_fused_bwd_work_ints",
               "wf_gemm_rowstats_parts"}
