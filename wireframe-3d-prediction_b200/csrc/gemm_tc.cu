@@ -81,6 +81,8 @@ struct Params {
     // SIDE kernels: pipeline stages actually used (the ring's unused tail, (6 - n_stages) * 32 KB, is the side warps' shared
     // memory) and the side-job segments (include/wf_b200.h, wf_side_seg)
     int n_stages, n_side;
+    unsigned long long hint_a, hint_b, hint_d;   // L2 eviction hints of the TMA transfers (2-SM form)
+    int n_workers;               // workers (CTAs, or CTA pairs) that take GEMM items; the rest of the grid only runs side jobs
     wf_side_seg side[WF_SIDE_MAX];
 };
 
@@ -114,6 +116,7 @@ struct Sched {
         const long long per = (total + n_workers - 1) / n_workers;
         u = (long long)worker * per;
         u_end = u + per < total ? u + per : total;
+        if (worker >= n_workers) { w = n_items; u = u_end = 0; }
     }
     __device__ __forceinline__ bool next(int& n_blk, int& mu, int& kb0, int& kb1) {
         if (streamk) {
@@ -212,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int crank = CL ? (int)ptx::cluster_ctarank() : 0;
     const int m_units = CL ? (p.tiles_m + 1) / 2 : p.tiles_m;
     const int w_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int w_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int w_step = p.n_workers;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -256,18 +259,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint32_t lbar = full_bar(stage) & ptx::PEER_BIT_MASK;
                         if (crank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * SB);
                         if (A_KM) {
-                            ptx::tma_load_2d_2sm(sa, &map_a, lbar, kb * BK, m_blk * BM);
+                            ptx::tma_load_2d_2sm_hint(sa, &map_a, lbar, kb * BK, m_blk * BM, p.hint_a);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BM / MNBOX; ++i)
-                                ptx::tma_load_2d_2sm(sa + i * BOX_BYTES, &map_a, lbar, m_blk * BM + i * MNBOX, kb * BK);
+                                ptx::tma_load_2d_2sm_hint(sa + i * BOX_BYTES, &map_a, lbar, m_blk * BM + i * MNBOX, kb * BK, p.hint_a);
                         }
                         if (B_KM) {
-                            ptx::tma_load_2d_2sm(sb, &map_b, lbar, kb * BK, n_blk * BN + crank * (BN / 2));
+                            ptx::tma_load_2d_2sm_hint(sb, &map_b, lbar, kb * BK, n_blk * BN + crank * (BN / 2), p.hint_b);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BN / MNBOX / 2; ++i)
-                                ptx::tma_load_2d_2sm(sb + i * BOX_BYTES, &map_b, lbar, n_blk * BN + crank * (BN / 2) + i * MNBOX, kb * BK);
+                                ptx::tma_load_2d_2sm_hint(sb + i * BOX_BYTES, &map_b, lbar, n_blk * BN + crank * (BN / 2) + i * MNBOX, kb * BK, p.hint_b);
                         }
                         if (++stage == NST) { stage = 0; phase ^= 1u; }
                         continue;
@@ -487,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        ptx::tma_store_2d(&map_d, smem_base + box_off, col0, row0);
+                        ptx::tma_store_2d_hint(&map_d, smem_base + box_off, col0, row0, p.hint_d);
                         ptx::bulk_commit();
                     }
                 } else if (full && !p.accumulate) {
@@ -715,7 +718,22 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     const int workers_max = mc ? sm_count() / 2 : sm_count();
     static const bool streamk_env = [] { const char* e = getenv("WF_B200_GEMM_STREAMK"); return e && e[0] == '1'; }();
     p.streamk = (streamk_env && accumulate && split_k > 1 && bias == nullptr && rowstats == nullptr) ? 1 : 0;
-    if (split_k > 1 && !p.streamk) {
+    // WF_B200_DW_ALIGN=1 (default off): split-K products with fewer output tiles than workers (the weight gradients: 8-32
+    // tiles, K = all points) on groups * tiles workers (64 of 74 pairs for 32 tiles) with a split count that is a multiple of
+    // the groups, so that a K range never straddles two waves.  Tried against the 1.4-1.8x DRAM reads of the weight gradients:
+    // the reads did not change (5.6 -> 5.5 GB, profiles/r02_gemm_traffic_*) -- the concurrent readers of a K range drift apart
+    // by more than L2 holds -- and neither did the time.
+    int group_workers = 0;
+    static const bool dw_align = [] { const char* e = getenv("WF_B200_DW_ALIGN"); return e && e[0] == '1'; }();
+    if (dw_align && accumulate && split_k > 1 && !p.streamk && det_work == nullptr) {
+        const long long tiles = (long long)m_units * p.tiles_n;
+        const int groups = (int)(workers_max / (tiles > 0 ? tiles : 1));
+        if (groups >= 1 && groups * tiles * 5 >= (long long)workers_max * 4) {       // at least 80 % of the workers stay busy
+            group_workers = (int)(groups * tiles);
+            split_k = ((split_k + groups - 1) / groups) * groups;
+        }
+    }
+    if (split_k > 1 && !p.streamk && group_workers == 0) {
         // The caller's split_k is a hint ("reduction-heavy").  Items are dealt round-robin, split index slowest, so the
         // CTAs running together read the same K range of both operands (L2 reuse); pick the smallest split whose
         // item count fills whole waves of workers (>= 95 %), which is what removes the wave-quantisation loss.
@@ -755,6 +773,17 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     p.tma_store = (tma_store_env && out_dtype == WF_BF16 && !p.accumulate && pool == nullptr && p.split_stride == 0) ? 1 : 0;
     CUtensorMap md = ma;                                         // placeholder when unused
     if (p.tma_store && (rc = make_store_map(&md, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd)) != WF_OK) return rc;
+    // L2 eviction priorities (WF_B200_L2_HINTS=1; default: all normal).  Tried: evict_last on operands that several
+    // concurrent tiles re-read, evict_first on the output and on once-read operands.  Measured (ncu, profiles/r02_gemm_traffic_*):
+    // DRAM reads went UP (weight gradients 5.5 -> 6.8 GB, the 2048-wide layer 3.8 -> 4.1 GB) -- pinning everything thrashes -- so
+    // the hints stay off.
+    static const bool hints = [] { const char* e = getenv("WF_B200_L2_HINTS"); return e && e[0] == '1'; }();
+    p.hint_a = p.hint_b = p.hint_d = ptx::L2_EVICT_NORMAL;
+    if (hints) {
+        p.hint_a = p.tiles_n > 1 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_FIRST;           // A tile: read by every N tile of its rows
+        p.hint_b = m_units > 1 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_FIRST;             // B tile: read by every M unit
+        p.hint_d = ptx::L2_EVICT_FIRST;
+    }
     p.n_stages = 6; p.n_side = 0;
     for (int i = 0; i < n_segs; ++i) {
         const wf_side_seg& sg = segs[i];
@@ -781,7 +810,9 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     if (p.n_side > 0 && p.n_stages == 6) p.n_stages = 5;
     long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
                                 : (long long)m_units * p.tiles_n * p.split_k;
-    const int workers = (int)(items < workers_max ? items : workers_max);
+    int workers = (int)(items < workers_max ? items : workers_max);
+    if (group_workers > 0 && group_workers < workers) workers = group_workers;
+    p.n_workers = workers;
     const int grid = mc ? 2 * workers : workers;
     const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
     if (p.n_side > 0) {
