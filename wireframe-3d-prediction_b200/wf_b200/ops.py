@@ -469,6 +469,19 @@ def gemm_bf16_pool(A, Wb, *, M, N, K, bias, points_per_cloud, row_offset, mask, 
     _count()
 
 
+# Data-parallel hook (wf_b200.parallel.GradAllReduce sets it): called with a list of gradient tensors as soon as they are FINAL
+# inside the encoder's backward -- layer by layer, while the remaining layers' GEMMs are still to run -- instead of only
+# when the whole autograd Function returns.  The tensors are the ones the Function later returns (autograd adopts them as
+# .grad), so they can be all-reduced in place right away.
+GRAD_READY_HOOK = None
+
+
+def _grads_ready(tensors):
+    hook = GRAD_READY_HOOK
+    if hook is not None:
+        hook([t for t in tensors if t is not None])
+
+
 # Test hook: (argmax_masked, argmax_unmasked) int32 [B, 512] used INSTEAD of the computed max-pool argmax for the gradient
 # routing of the next EncoderPointMLP_TC.forward.  The parity tests inject the reference's indices with it, so that a
 # flipped argmax (a legitimate discontinuity under bf16-sized perturbations) cannot hide a gradient error.
@@ -629,6 +642,9 @@ def _enc_mlp_backward(dh_top, hs, zs, means, rstds, layers, sms):
             split = max(1, min((mc + 63) // 64, (2 * sms + tiles - 1) // tiles))
             gemm_bf16(dzs[li][r0:r1], hs[li][r0:r1], M=Nn, N=K, K=mc, kmajor=False, out=dWs[li], accumulate=True, split_k=split,
                       side=segs)
+            if c == nc - 1:                                  # every chunk of this layer's LayerNorm backward and dW is enqueued
+                k = li + 2
+                _grads_ready([grads[f"W{k}"], grads[f"b{k}"], grads[f"g{k}"], grads[f"be{k}"]])
     return grads, dh1
 
 
@@ -831,6 +847,7 @@ class EncoderPointMLP_TC(torch.autograd.Function):
                  _p(dbar), _p(W5c), _p(hs[3]), B, N, C5, K5, _p(work), _p(dh), _p(dW5), _p(db5), _s())
             _count(4)
             grads["W5"], grads["b5"] = dW5, db5
+            _grads_ready([dW5, db5])
         else:
             dz = torch.empty(M, C5, device=dev, dtype=torch.bfloat16)
             db5 = zeros_f32(C5, device=dev)

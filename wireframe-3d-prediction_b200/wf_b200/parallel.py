@@ -92,6 +92,11 @@ class GradAllReduce:
         self._stream = None
         self._built = False
         self._bucket_of: Dict[torch.nn.Parameter, dict] = {}
+        self._early_ptrs = set()
+        self._armed = False
+        if self.world > 1:
+            from . import ops
+            ops.GRAD_READY_HOOK = self._early
         self._hooked = set()
         for p in module.parameters():
             if p.requires_grad:
@@ -110,6 +115,22 @@ class GradAllReduce:
         else:
             self._order = []
         self._handles = []
+        self._early_ptrs = set()
+        self._armed = True
+
+    def _early(self, tensors: List[torch.Tensor]) -> None:
+        """ops.GRAD_READY_HOOK: gradient tensors that are final INSIDE the encoder's backward (one layer at a time) are
+        reduced at once, under the GEMMs of the remaining layers, instead of in the bucket that only fills when the whole
+        Function has returned (its 21 MB were the exposed tail of the step).  They are skipped when their bucket fires."""
+        if self.world == 1 or not self._built or not tensors or not self._armed:
+            return                       # only between zero() and finish(): another model's backward must not start a collective
+        # aliases, not the tensors themselves: the NCCL work objects keep their operands alive, and autograd adopts a returned
+        # gradient as .grad without a copy only while nobody else references that tensor object
+        self._launch([t.detach() for t in tensors])
+        self._early_ptrs.update(t.data_ptr() for t in tensors)
+
+    def _not_early(self, grads: List[torch.Tensor]) -> List[torch.Tensor]:
+        return [g for g in grads if g.data_ptr() not in self._early_ptrs]
 
     def _on_grad(self, p: torch.nn.Parameter) -> None:
         if self.world == 1:
@@ -125,7 +146,7 @@ class GradAllReduce:
             raise RuntimeError("GradAllReduce: a parameter received a second gradient before finish(); the bucket it belongs to "
                                "has already been handed to NCCL (one backward per zero()/finish() pair)")
         if b["pending"] == 0:
-            self._launch([q.grad for q in b["params"] if q.grad is not None])
+            self._launch(self._not_early([q.grad for q in b["params"] if q.grad is not None]))
 
     def _reduce_list(self, tensors: List[torch.Tensor]) -> None:
         """One grouped in-place SUM all-reduce over `tensors` (NCCL); per-tensor calls on backends without grouping."""
@@ -166,6 +187,7 @@ class GradAllReduce:
     def finish(self) -> None:
         """Call after backward() -- ONE backward per zero()/finish() pair.  First step: fixes the buckets from the observed
         gradient order and reduces everything at once; later steps: waits for the in-flight bucket reductions."""
+        self._armed = False
         if self.world == 1:
             return
         self._check_registered()
@@ -175,7 +197,7 @@ class GradAllReduce:
         else:
             for b in self.buckets:                  # a bucket whose hooks did not all fire (a parameter without gradient)
                 if 0 < b["pending"] < b["n"] or (b["pending"] == b["n"] and any(p.grad is not None for p in b["params"])):
-                    self._launch([q.grad for q in b["params"] if q.grad is not None]); b["pending"] = 0
+                    self._launch(self._not_early([q.grad for q in b["params"] if q.grad is not None])); b["pending"] = 0
         for h in self._handles:
             h.wait()
         if self._stream is not None:
@@ -203,3 +225,6 @@ class GradAllReduce:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        from . import ops
+        if ops.GRAD_READY_HOOK == self._early:
+            ops.GRAD_READY_HOOK = None
