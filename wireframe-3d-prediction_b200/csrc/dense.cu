@@ -10,23 +10,26 @@ namespace dense {
 // ------------------------------------------------------------------------------------------
 // C = alpha * op(A) * op(B) + beta * C + bias      64x64 CTA tile, 16-deep k-slab, 4x4 per thread
 // ------------------------------------------------------------------------------------------
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TK = 16;
 
-template <bool TA, bool TB>
+// R: register tile R x R per thread, CTA tile 16R x 16R (R = 4: 64 x 64; R = 2: 32 x 32 for products whose output has too few
+// 64 x 64 tiles to occupy the GPU -- the 128-row pooled products ran on 16 CTAs)
+template <bool TA, bool TB, int R>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                 const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc,
                 const float* __restrict__ bias, int k_chunk) {
+    constexpr int TM = 16 * R, TN = 16 * R;
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, each 4 x 4 outputs
-    float acc[4][4];
+    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, each R x R outputs
+    float acc[R][R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
 
     // split-K: blockIdx.z owns [kz0, kz1) and accumulates atomically (host pre-zeroes C when beta == 0)
     const int kz0 = blockIdx.z * k_chunk;
@@ -34,10 +37,10 @@ gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, i
     for (int k0 = kz0; k0 < K; k0 += TK) {
         // ---- stage A (op(A) is M x K)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < R; ++i) {
             int m, k;
-            if (!TA) { k = tid & 15; m = (tid >> 4) + 16 * i; }      // k contiguous in memory
-            else     { m = tid & 63; k = (tid >> 6) + 4 * i; }       // m contiguous in memory
+            if (!TA) { k = tid & 15; m = (tid >> 4) + 16 * i; }                 // k contiguous in memory
+            else     { m = tid & (TM - 1); k = tid / TM + (256 / TM) * i; }     // m contiguous in memory
             const int gm = m0 + m, gk = k0 + k;
             float v = 0.f;
             if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
@@ -45,10 +48,10 @@ gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, i
         }
         // ---- stage B (op(B) is K x N)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < R; ++i) {
             int n, k;
-            if (!TB) { n = tid & 63; k = (tid >> 6) + 4 * i; }       // n contiguous
-            else     { k = tid & 15; n = (tid >> 4) + 16 * i; }      // k contiguous
+            if (!TB) { n = tid & (TN - 1); k = tid / TN + (256 / TN) * i; }     // n contiguous
+            else     { k = tid & 15; n = (tid >> 4) + 16 * i; }                 // k contiguous
             const int gn = n0 + n, gk = k0 + k;
             float v = 0.f;
             if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
@@ -57,25 +60,25 @@ gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, i
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            float a[4], b[4];
+            float a[R], b[R];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+            for (int i = 0; i < R; ++i) a[i] = As[k][ty * R + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+            for (int j = 0; j < R; ++j) b[j] = Bs[k][tx * R + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < R; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < R; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < R; ++i) {
+        const int gm = m0 + ty * R + i;
         if (gm >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
+        for (int j = 0; j < R; ++j) {
+            const int gn = n0 + tx * R + j;
             if (gn >= N) continue;
             float v = alpha * acc[i][j];
             float* dst = C + (size_t)gm * ldc + gn;
@@ -477,7 +480,10 @@ extern "C" int wf_gemm_f32(int transA, int transB, int M, int N, int K, float al
     using namespace wf::dense;
     if (M <= 0 || N <= 0) return WF_OK;
     WF_CHECK_ARG(K >= 0 && lda > 0 && ldb > 0 && ldc >= N, "wf_gemm_f32: bad dims");
-    dim3 grid(cdiv(N, TN), cdiv(M, TM));
+    // few 64 x 64 tiles: 32 x 32 tiles put 4x the CTAs on the product (same summation order per output: results are identical)
+    const bool small = (long long)cdiv(N, 64) * cdiv(M, 64) * 2 <= sm_count();
+    const int T = small ? 32 : 64;
+    dim3 grid(cdiv(N, T), cdiv(M, T));
     cudaStream_t s = as_stream(stream);
     // split-K when the output is small and the reduction long (weight gradients of the edge head: K = #edges)
     int split = 1;
@@ -495,10 +501,13 @@ extern "C" int wf_gemm_f32(int transA, int transB, int M, int N, int K, float al
         if (beta == 0.f) WF_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s));
     }
     grid.z = split;
-    if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
-    else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
-    else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
-    else gemm_f32_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
+#define WF_GF(TA_, TB_) do { if (small) gemm_f32_kernel<TA_, TB_, 2><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk); \
+                             else gemm_f32_kernel<TA_, TB_, 4><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk); } while (0)
+    if (!transA && !transB) WF_GF(false, false);
+    else if (!transA && transB) WF_GF(false, true);
+    else if (transA && !transB) WF_GF(true, false);
+    else WF_GF(true, true);
+#undef WF_GF
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

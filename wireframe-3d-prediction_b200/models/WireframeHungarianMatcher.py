@@ -9,7 +9,7 @@ from wf_b200._lib import LSAP_INFEASIBLE, LSAP_INVALID, call
 
 
 def _raise_status(status):
-    st = status.tolist()
+    st = status.tolist() if torch.is_tensor(status) else list(status)
     if any(s == LSAP_INFEASIBLE for s in st):
         raise ValueError("cost matrix is infeasible")
     if any(s == LSAP_INVALID for s in st):
@@ -17,13 +17,16 @@ def _raise_status(status):
 
 
 def _to_pairs(col, sizes, nq):
-    """col_of_row (B, nq) on host -> scipy-style (row_idx, col_idx) int64 tensors (rows ascending)."""
-    out = []
-    for b, t in enumerate(sizes):
-        c = col[b, :nq]
-        rows = torch.nonzero(c >= 0).flatten() if t < nq else torch.arange(nq)
-        out.append((rows.to(torch.int64), c[rows].to(torch.int64)))
-    return out
+    """col_of_row (B, nq) host int array -> scipy-style (row_idx, col_idx) int64 tensors (rows ascending).  One vectorised
+    pass over the whole batch: the matched (row, column) pairs of all samples come out of a single nonzero, split per sample."""
+    import numpy as np
+    col = np.asarray(col)[:, :nq]
+    b_idx, r_idx = np.nonzero(col >= 0)                       # row-major: samples in order, rows ascending inside each
+    c_idx = col[b_idx, r_idx].astype(np.int64)
+    cuts = np.cumsum(np.bincount(b_idx, minlength=col.shape[0]))[:-1]
+    rows = np.split(r_idx.astype(np.int64), cuts)
+    cols = np.split(c_idx, cuts)
+    return [(torch.from_numpy(np.ascontiguousarray(r)), torch.from_numpy(np.ascontiguousarray(c))) for r, c in zip(rows, cols)]
 
 
 class WireframeHungarianMatcher(nn.Module):
@@ -56,8 +59,10 @@ class WireframeHungarianMatcher(nn.Module):
         nr = torch.full((bs,), nq, dtype=torch.int32, device=dev)
         nc = torch.tensor(sizes, dtype=torch.int32, device=dev)
         col, status = ops.lsap_batched(cost, nr, nc)
-        _raise_status(status)
-        return _to_pairs(col.cpu(), sizes, nq)
+        # ONE device->host copy (assignments and solver status together) and no per-sample tensor ops on the way back
+        host = torch.cat([col, status.view(bs, 1)], dim=1).cpu().numpy()
+        _raise_status(host[:, -1])
+        return _to_pairs(host[:, :-1], sizes, nq)
 
 
 def build_wireframe_matcher(cost_vertex=1.0, cost_existence=1.0):
