@@ -266,6 +266,18 @@ int wf_gemm_bf16_side(const void* A, int lda, int a_kmajor, const void* B, int l
                       int split_k, float* rowstats, int pool_n, int pool_row_offset, int pool_index_offset,
                       const uint8_t* pool_mask, uint64_t* pool_max_u, uint64_t* pool_max_m,
                       const wf_side_seg* segs, int n_segs, wf_stream_t stream);
+
+/* Linear + LayerNorm + ReLU of models/PointNetEncoder.py:37-40 in ONE launch: Z = A * B^T + bias (bf16, stored: the backward
+ * needs it) exactly as wf_gemm_bf16 with row statistics, and H = relu(LN(Z)) produced by the side warps of the same kernel
+ * from the 256-row units of Z that have just been completed by all their N tiles -- read back from L2, not from DRAM.
+ * mean / rstd [M] are finalised in-kernel (same expression as wf_stats_finalize) and written for the backward.
+ * `done`: ceil(M / 256) int32 counters, zeroed by the caller before every launch.  N in {1024, 2048}, M >= 256, K-major
+ * operands.  Z, H, mean, rstd are bit-identical to wf_gemm_bf16 + wf_stats_finalize + wf_ln_relu_bf16_fwd.  May carry
+ * further side segments (other rows' passes), executed after the own-output work. */
+int wf_gemm_bf16_ownln(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                       const float* bias, void* Z, float* rowstats, const float* gamma, const float* beta,
+                       void* H, float* mean, float* rstd, float eps, int32_t* done,
+                       const wf_side_seg* segs, int n_segs, wf_stream_t stream);
 /* Backward of the four pools THROUGH the final Linear (W [C,K] fp32, h [B*N,K] bf16 its input) without dense GEMMs:
  * the pooled gradients are per-cloud constants plus <= 2C single entries at the argmax rows (train.py:140 autograd
  * reaches the same numbers through a dense (B*N,C) gradient).  dbar[2][B][K] = [g_mean_u; g_avg_m] W (caller).

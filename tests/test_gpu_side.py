@@ -168,3 +168,31 @@ def test_encoder_with_side_jobs_equals_encoder_without(ops, chunks):
         if k.startswith("mlp."):
             assert rel_err(res["side"][1][k], g) < 2e-3, k
             assert float((res["side"][1][k].double() - g.double()).norm() / g.double().norm()) < 5e-4, k
+
+
+@pytest.mark.parametrize("M,N,K", [(256 * 5 + 77, 1024, 512), (256 * 40, 2048, 1024), (300000, 1024, 512), (40000, 2048, 1024)])
+def test_own_output_layernorm_is_bit_identical(ops, M, N, K):
+    """wf_gemm_bf16_ownln: Linear, row statistics and LayerNorm+ReLU in one launch -- the side warps normalise each 256-row
+    unit once all its N tiles are stored, reading it back through L2.  Z, mean, rstd and H must equal the three-kernel
+    sequence (wf_gemm_bf16 + wf_stats_finalize + wf_ln_relu_bf16_fwd) bit for bit, launch after launch (a missed
+    dependency would show as stale rows)."""
+    from wf_b200.ops import call, _p, _s
+    A, W, bias = _gemm_inputs(M, N, K, 11)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    gamma = (1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)).contiguous()
+    beta = (0.1 * torch.randn(N, device="cuda", generator=g)).contiguous()
+    parts = call("wf_gemm_rowstats_parts", N)
+    z0 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16); st0 = torch.empty(parts, M, 2, device="cuda")
+    mean0 = torch.empty(M, device="cuda"); rstd0 = torch.empty(M, device="cuda"); h0 = torch.empty_like(z0)
+    ops.gemm_bf16(A, W, M=M, N=N, K=K, bias=bias, out=z0, rowstats=st0)
+    call("wf_stats_finalize", _p(st0), M, N, parts, 1e-5, _p(mean0), _p(rstd0), _s())
+    call("wf_ln_relu_bf16_fwd", _p(z0), _p(mean0), _p(rstd0), _p(gamma), _p(beta), _p(h0), M, N, _s())
+    for rep in range(3):
+        z1 = torch.full_like(z0, float("nan")); st1 = torch.empty_like(st0)
+        mean1 = torch.full_like(mean0, float("nan")); rstd1 = torch.full_like(rstd0, float("nan")); h1 = torch.full_like(z0, float("nan"))
+        ops.gemm_bf16_ownln(A, W, M=M, N=N, K=K, bias=bias, z=z1, rowstats=st1, gamma=gamma, beta=beta, h=h1, mean=mean1, rstd=rstd1)
+        torch.cuda.synchronize()
+        assert torch.equal(z1.view(torch.int16), z0.view(torch.int16)), "Z differs"
+        assert torch.equal(mean1, mean0) and torch.equal(rstd1, rstd0), "row statistics differ"
+        bad = (h1.view(torch.int16) != h0.view(torch.int16)).any(dim=1).nonzero().flatten()
+        assert bad.numel() == 0, f"H differs on {bad.numel()} rows (first {bad[:8].tolist()}) in repetition {rep}"

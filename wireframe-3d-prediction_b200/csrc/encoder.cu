@@ -2,6 +2,7 @@
 // (memory-bound, fp32, fused Linear+LayerNorm+ReLU), LayerNorm statistics finalisation, weight
 // staging casts, and the four pooled reductions with their backward.
 #include "wf_common.cuh"
+#include "ln_side.cuh"
 
 #include <stdlib.h>
 
@@ -624,11 +625,9 @@ __global__ void stats_finalize_kernel(const float2* __restrict__ st, int M, int 
                                       float* __restrict__ mean, float* __restrict__ rstd) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
-    float s1 = 0.f, s2 = 0.f;
-    for (int p = 0; p < parts; ++p) { const float2 t = st[(size_t)p * M + i]; s1 += t.x; s2 += t.y; }     // fixed order
-    const float mu = s1 * invC;
-    const float var = fmaxf(s2 * invC - mu * mu, 0.f);
-    mean[i] = mu; rstd[i] = rsqrtf(var + eps);
+    float mu, rs;
+    lnb::stats_from_parts(st + i, (size_t)M, parts, invC, eps, mu, rs);
+    mean[i] = mu; rstd[i] = rs;
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {

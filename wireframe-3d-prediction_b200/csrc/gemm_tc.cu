@@ -81,6 +81,14 @@ struct Params {
     // SIDE kernels: pipeline stages actually used (the ring's unused tail, (6 - n_stages) * 32 KB, is the side warps' shared
     // memory) and the side-job segments (include/wf_b200.h, wf_side_seg)
     int n_stages, n_side;
+    // SIDE kernels, own-output LayerNorm (models/PointNetEncoder.py:38-39 fused behind the Linear of the SAME launch): the side
+    // warps normalise each 256-row unit of D as soon as all its N tiles are stored -- the tile is still in L2, so the
+    // LayerNorm pass reads nothing from DRAM.  own_done[m unit] counts the epilogue warps (2 CTAs x 8 per tile) whose stores
+    // of that unit are complete; row statistics are finalised in-kernel from `rowstats` and also written out (backward).
+    int own_kind;                // 0 = off, 1 = h = relu(LN(D)) (bf16)
+    const float* own_gamma; const float* own_beta;
+    void* own_h; float* own_mean; float* own_rstd; float own_eps;
+    int* own_done;
     unsigned long long hint_a, hint_b, hint_d;   // L2 eviction hints of the TMA transfers (2-SM form)
     int n_workers;               // workers (CTAs, or CTA pairs) that take GEMM items; the rest of the grid only runs side jobs
     wf_side_seg side[WF_SIDE_MAX];
@@ -158,6 +166,57 @@ constexpr int SIDE_SMEM_FWD_COLSUM_1024 = 2 * 2 * 1024 * 4;
 constexpr int SIDE_SMEM_BWD_1024 = lnb::ln_bwd_side_smem<128, SIDE_THREADS, 2, 3, false>();
 constexpr int SIDE_SMEM_BWD_2048 = lnb::ln_bwd_side_smem<256, SIDE_THREADS, 2, 2, true>();
 static_assert(SIDE_SMEM_FWD_COLSUM_1024 <= 32768 && SIDE_SMEM_BWD_1024 <= 32768 && SIDE_SMEM_BWD_2048 <= 65536, "side smem");
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Own-output LayerNorm forward (Params::own_*): this CTA's side warps walk the CTA's own tile sequence; for every tile they
+// wait until the whole 256-row unit it belongs to has been stored by all the CTAs that hold its N tiles, then normalise
+// their slice of the unit's rows (256 rows / (2 * tiles_n) CTAs) over the full width N.
+template <int C8>
+__device__ __forceinline__ void own_ln_forward(const Params& p, int tid, uint8_t* smem, int m_units, int w_first, int crank) {
+    Sched sched(p, m_units, w_first, p.n_workers);
+    const int slices = 2 * p.tiles_n, R = (2 * BM) / slices;              // rows of a unit per CTA (16 .. 128)
+    const int target = p.tiles_n * 2 * EPI_WARPS;
+    float* st = reinterpret_cast<float*>(smem);                            // [R][2] mean, rstd  (2 * tiles_n = C8 / 16 row-statistic parts)
+    const float invC = 1.0f / (float)p.N;
+    int n_blk, mu, kb0, kb1;
+    while (sched.next(n_blk, mu, kb0, kb1)) {
+        const long long row0 = (long long)mu * (2 * BM) + (long long)(n_blk * 2 + crank) * R;
+        const int rows = (int)(row0 + R <= p.M ? R : (p.M > row0 ? p.M - row0 : 0));
+        if (tid == 0) {
+            const int* flag = p.own_done + mu;
+            if (ld_acquire_gpu(flag) < target) {
+                const uint64_t t0 = ptx::globaltimer_ns();
+                while (ld_acquire_gpu(flag) < target) {
+                    __nanosleep(256);
+                    if (ptx::globaltimer_ns() - t0 > WF_MBAR_TIMEOUT_NS) {
+                        printf("wf_b200: own-output LayerNorm wait timed out (block %d unit %d: %d of %d)\n", (int)blockIdx.x, mu,
+                               ld_acquire_gpu(flag), target);
+                        __trap();
+                    }
+                }
+            }
+        }
+        lnb::pass_sync<SIDE_THREADS>(SIDE_BAR);
+        fence_proxy_async_global();                                        // D was written by the copy engines (async proxy)
+        if (tid < rows) {
+            float m_, r_;
+            lnb::stats_from_parts_n<C8 / 16>(reinterpret_cast<const float2*>(p.rowstats) + (row0 + tid), (size_t)p.M, invC, p.own_eps, m_, r_);
+            st[2 * tid] = m_; st[2 * tid + 1] = r_;
+            p.own_mean[row0 + tid] = m_; p.own_rstd[row0 + tid] = r_;
+        }
+        lnb::pass_sync<SIDE_THREADS>(SIDE_BAR);
+        if (rows > 0)
+            lnb::ln_fwd_rows_l2<C8, SIDE_THREADS>(static_cast<const uint4*>(p.D), static_cast<uint4*>(p.own_h), p.own_gamma, p.own_beta,
+                                                  st, row0, rows, tid);
+        lnb::pass_sync<SIDE_THREADS>(SIDE_BAR);                            // st is rewritten for the next tile
+    }
+}
 
 __device__ __forceinline__ void run_side_jobs(const Params& p, int tid, uint8_t* smem) {
     const int worker = blockIdx.x, n_workers = gridDim.x;
@@ -241,6 +300,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (SIDE && warp >= 12) {
         // ------------------------------------------------------------------ side jobs
         asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+        if (p.own_kind == 1) {
+            if (p.N == 1024) own_ln_forward<128>(p, (int)threadIdx.x - NTHREADS, smem + NST * SB, m_units, w_first, crank);
+            else own_ln_forward<256>(p, (int)threadIdx.x - NTHREADS, smem + NST * SB, m_units, w_first, crank);
+        }
         run_side_jobs(p, (int)threadIdx.x - NTHREADS, smem + NST * SB);
     } else if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -364,6 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (warp - 4) * STG_TILE;
         float* bias_slot = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES) + (warp - 4) * 32;
         int acc = 0; uint32_t acc_phase = 0;
+        int own_prev = -1;                                       // own-output LayerNorm: unit whose completion is still to be signalled
         Sched sched(p, m_units, w_first, w_step);
         int n_blk, mu, kb0, kb1;
         while (sched.next(n_blk, mu, kb0, kb1)) {
@@ -379,6 +443,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 pool_rows = min(32, p.M - row0);
                 pool_b0 = (p.pool_row0 + row0) / p.pool_n;
                 pool_rb = (pool_b0 + 1) * p.pool_n - (p.pool_row0 + row0);   // rows >= pool_rb belong to the next cloud
+            }
+            if (SIDE && p.own_kind != 0 && own_prev >= 0) {
+                // Tell the side warps that this warp's part of the PREVIOUS tile's unit is in global memory.  Done here, one
+                // tile late and before the wait for the next accumulator: the bulk stores and the row statistics of that tile
+                // were issued a whole tile ago, so neither the wait_group nor the fence has anything left to wait for.
+                __syncwarp();                                    // orders the other lanes' row-statistics stores before lane 0's release
+                if (lane == 0) {
+                    ptx::bulk_wait<0>();
+                    fence_proxy_async_global();
+                    __threadfence();
+                    atomicAdd(p.own_done + own_prev, 1);
+                }
+                own_prev = -1;
             }
             const bool add_bias = p.bias != nullptr && kb0 == 0;       // split-K: the first K range carries the bias
             // Bias: lane j fetches the value of column j of the NEXT chunk one chunk ahead (one register), so the load's
@@ -559,8 +636,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 else ptx::mbar_arrive(tempty_bar(acc));
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (SIDE && p.own_kind != 0) own_prev = mu;
         }
         if (p.tma_store && lane == 0) ptx::bulk_wait<0>();       // this warp's stores are complete before the CTA may exit
+        if (SIDE && p.own_kind != 0 && own_prev >= 0) {
+            __syncwarp();
+            if (lane == 0) { fence_proxy_async_global(); __threadfence(); atomicAdd(p.own_done + own_prev, 1); }
+        }
     }
 
     ptx::tc_fence_before();
@@ -677,12 +759,13 @@ static int cluster_mode() {
 }
 
 struct PoolArgs { int n, row0, idx0; const uint8_t* mask; unsigned long long* max_u; unsigned long long* max_m; };
+struct OwnArgs { const float* gamma; const float* beta; void* h; float* mean; float* rstd; float eps; int* done; };
 
 // esz 2: bf16 operands; esz 4: fp32 operands multiplied as tf32
 static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, int M, int N, int K,
                    const float* bias, void* D, int ldd, int out_dtype, int accumulate, int split_k, float* rowstats,
                    cudaStream_t stream, const PoolArgs* pool = nullptr, float* det_work = nullptr, long long det_work_floats = 0,
-                   const wf_side_seg* segs = nullptr, int n_segs = 0) {
+                   const wf_side_seg* segs = nullptr, int n_segs = 0, const OwnArgs* own = nullptr) {
     const int al = 16 / esz;                                     // elements per 16 bytes
     WF_CHECK_ARG(M > 0 && N > 0 && K > 0, "wf_gemm_tc: empty problem M=%d N=%d K=%d", M, N, K);
     WF_CHECK_ARG(lda % al == 0 && ldb % al == 0, "wf_gemm_tc: lda/ldb must be multiples of %d elements (16-byte TMA strides)", al);
@@ -807,7 +890,18 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
         if (st < p.n_stages) p.n_stages = st;
         p.side[p.n_side++] = sg;
     }
-    if (p.n_side > 0 && p.n_stages == 6) p.n_stages = 5;
+    p.own_kind = 0; p.own_gamma = p.own_beta = nullptr; p.own_h = nullptr; p.own_mean = p.own_rstd = nullptr; p.own_eps = 0.f; p.own_done = nullptr;
+    if (own != nullptr) {
+        WF_CHECK_ARG(mode == 2 && esz == 2 && a_kmajor && b_kmajor && p.tma_store && rowstats != nullptr && p.split_k == 1 &&
+                     (N == 1024 || N == 2048) && N % BN == 0,
+                     "wf_gemm_bf16_ownln: needs the 2-SM bf16 K-major form with row statistics, M >= 256, N in {1024, 2048}");
+        WF_CHECK_ARG(own->gamma && own->beta && own->h && own->mean && own->rstd && own->done, "wf_gemm_bf16_ownln: null pointer");
+        WF_CHECK_ARG(((reinterpret_cast<uintptr_t>(own->h) | reinterpret_cast<uintptr_t>(own->gamma) | reinterpret_cast<uintptr_t>(own->beta)) & 15) == 0
+                     && ldd == N, "wf_gemm_bf16_ownln: 16-byte alignment and a dense D (ldd == N) required");
+        p.own_kind = 1; p.own_gamma = own->gamma; p.own_beta = own->beta; p.own_h = own->h; p.own_mean = own->mean; p.own_rstd = own->rstd;
+        p.own_eps = own->eps; p.own_done = own->done;
+    }
+    if ((p.n_side > 0 || p.own_kind != 0) && p.n_stages == 6) p.n_stages = 5;
     long long items = p.streamk ? (long long)m_units * p.tiles_n * p.nkb          // units: any worker count up to this
                                 : (long long)m_units * p.tiles_n * p.split_k;
     int workers = (int)(items < workers_max ? items : workers_max);
@@ -815,7 +909,7 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     p.n_workers = workers;
     const int grid = mc ? 2 * workers : workers;
     const int key = (esz == 4 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
-    if (p.n_side > 0) {
+    if (p.n_side > 0 || p.own_kind != 0) {
         // every CTA of the launch takes its share of the side rows: always the full grid, whatever the GEMM's item count
         const int sgrid = 2 * workers_max;
         rc = a_kmajor ? launch<2, true, true, 2, true>(ma, mb, md, p, sgrid, stream) : launch<2, false, false, 2, true>(ma, mb, md, p, sgrid, stream);
@@ -878,6 +972,15 @@ extern "C" int wf_gemm_bf16_side(const void* A, int lda, int a_kmajor, const voi
     }
     return wf::tc::gemm_tc(2, A, lda, a_kmajor, B, ldb, b_kmajor, M, N, K, bias, D, ldd, out_dtype, accumulate, split_k, rowstats,
                            wf::as_stream(stream), nullptr, nullptr, 0, segs, n_segs);
+}
+
+extern "C" int wf_gemm_bf16_ownln(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, void* Z,
+                                  float* rowstats, const float* gamma, const float* beta, void* H, float* mean, float* rstd,
+                                  float eps, int32_t* done, const wf_side_seg* segs, int n_segs, wf_stream_t stream) {
+    WF_CHECK_ARG(n_segs >= 0 && (n_segs == 0 || segs != nullptr), "wf_gemm_bf16_ownln: bad segment list");
+    wf::tc::OwnArgs oa{gamma, beta, H, mean, rstd, eps, done};
+    return wf::tc::gemm_tc(2, A, lda, 1, B, ldb, 1, M, N, K, bias, Z, N, WF_BF16, 0, 1, rowstats, wf::as_stream(stream), nullptr,
+                           nullptr, 0, segs, n_segs, &oa);
 }
 
 extern "C" int wf_gemm_tf32(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, int M, int N,

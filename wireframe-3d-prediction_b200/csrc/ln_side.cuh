@@ -48,6 +48,57 @@ __device__ __forceinline__ uint4 ln_relu8(const uint4& u, float mu, float rs, co
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// (sum, sum of squares) partials of a row, added in part order -> (mean, rstd); ONE expression shared by wf_stats_finalize and the
+// in-kernel finalisation of the GEMM's own-output LayerNorm, so that both give the same bits
+__device__ __forceinline__ void stats_from_parts(const float2* __restrict__ st, size_t stride, int parts, float invC, float eps,
+                                                 float& mu, float& rs) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = 0; p < parts; ++p) { const float2 t = __ldcg(st + (size_t)p * stride); s1 += t.x; s2 += t.y; }     // fixed order
+    mu = s1 * invC;
+    const float var = fmaxf(s2 * invC - mu * mu, 0.f);
+    rs = rsqrtf(var + eps);
+}
+
+// the same with a compile-time part count: all loads in flight at once (the in-kernel finalisation is latency-bound)
+template <int PARTS>
+__device__ __forceinline__ void stats_from_parts_n(const float2* __restrict__ st, size_t stride, float invC, float eps, float& mu, float& rs) {
+    float2 t[PARTS];
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) t[p] = __ldcg(st + (size_t)p * stride);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) { s1 += t[p].x; s2 += t[p].y; }                                                    // fixed order
+    mu = s1 * invC;
+    const float var = fmaxf(s2 * invC - mu * mu, 0.f);
+    rs = rsqrtf(var + eps);
+}
+
+// h = relu(LN(z)) on rows [row0, row0 + rows) of a [*, C8 * 8] bf16 tensor, statistics (mean, rstd) per local row in shared memory;
+// NT threads, z read through L2 (ld.global.cg: the rows were written moments ago by other SMs of the same launch).  The slices
+// are short (16-64 rows) and every load is an L2 round trip, so UN rows of every channel group are requested before any is used.
+template <int C8, int NT>
+__device__ __forceinline__ void ln_fwd_rows_l2(const uint4* __restrict__ z, uint4* __restrict__ h, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, const float* st, long long row0, int rows, int tid) {
+    constexpr int G = C8 / NT, UN = 8;
+    static_assert(C8 % NT == 0 && G >= 1 && G <= 2, "channel groups per thread");
+    u64 gm[G][4], bt[G][4];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { load_pairs(gamma + (tid + g * NT) * 8, gm[g]); load_pairs(beta + (tid + g * NT) * 8, bt[g]); }
+    for (int r = 0; r < rows; r += UN) {
+        uint4 u[G][UN];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < UN; ++j)
+                u[g][j] = r + j < rows ? __ldcg(z + (row0 + r + j) * C8 + tid + g * NT) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < UN; ++j)
+                if (r + j < rows) h[(row0 + r + j) * C8 + tid + g * NT] = ln_relu8(u[g][j], st[2 * (r + j)], st[2 * (r + j) + 1], gm[g], bt[g]);
+    }
+}
+
 // barrier over the NT threads that execute a pass together: the whole CTA (stand-alone) or the side warps (named barrier)
 template <int NT>
 __device__ __forceinline__ void pass_sync(int bar_id) {

@@ -448,6 +448,23 @@ def gemm_bf16(A, B, *, M, N, K, kmajor=True, bias=None, out, accumulate=False, s
     return out
 
 
+def gemm_bf16_ownln(A, Wb, *, M, N, K, bias, z, rowstats, gamma, beta, h, mean, rstd, side=None):
+    """Linear + LayerNorm + ReLU in one launch (wf_gemm_bf16_ownln): z = A Wb^T + bias (bf16, kept for the backward) and
+    h = relu(LN(z)) by the kernel's side warps from the freshly stored tiles (L2), mean / rstd written."""
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    done = torch.zeros((M + 255) // 256, device=A.device, dtype=torch.int32)
+    arr, n = _seg_array(side or [])
+    call("wf_gemm_bf16_ownln", _p(A), A.stride(0), _p(Wb), Wb.stride(0), M, N, K, _p(bias), _p(z), _p(rowstats), _p(gamma), _p(beta),
+         _p(h), _p(mean), _p(rstd), 1e-5, _p(done), ctypes.byref(arr), n, _s())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K))
+    _count(2)
+
+
 def gemm_bf16_pool(A, Wb, *, M, N, K, bias, points_per_cloud, row_offset, mask, packed, index_offset=0, side=None):
     """Final per-point Linear whose epilogue max-pools instead of storing (wf_gemm_bf16_pool).  packed: int64 [2, clouds, N]
     (zero-initialised by the caller; [0] = all rows, [1] = valid rows)."""
