@@ -244,6 +244,54 @@ def test_edge_pair_and_out(ops):
         assert_close(a.grad, r.grad, 3e-4, f"edge grad {n}")
 
 
+@pytest.mark.parametrize("hidden,heads", [(256, 4), (128, 8), (1024, 8), (512, 4)])
+def test_edge_predictor_other_widths(ops, hidden, heads):
+    """models/EdgePredictor.py:19 accepts hidden_dim / num_heads; the drop-in runs the same kernels instantiated for other widths.
+    Held to a float64 restatement of the reference forward (models/EdgePredictor.py:91-140) on the same parameters, forward
+    and every parameter gradient."""
+    from models.EdgePredictor import EdgePredictor
+    torch.manual_seed(8)
+    m = EdgePredictor(vertex_dim=3, hidden_dim=hidden, num_heads=heads).cuda().eval()   # eval: the three dropout sites off
+    B, V = 3, 11
+    verts = torch.rand(B, V, 3, device="cuda")
+    vg = verts.clone().requires_grad_(True)
+    probs, idx = m(vg)
+    go = torch.randn_like(probs)
+    probs.backward(go)
+    got = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    md = EdgePredictor.__new__(EdgePredictor)
+    torch.nn.Module.__init__(md)
+    import copy
+    for name in ("vertex_proj", "attention", "spatial_proj", "edge_mlp"):
+        setattr(md, name, copy.deepcopy(getattr(m, name)).double())
+    vd = verts.double().requires_grad_(True)
+    f = md.vertex_proj(vd)
+    a, _ = md.attention(f, f, f)
+    f = f + a
+    iu = torch.triu_indices(V, V, offset=1, device="cuda")
+    v1, v2 = vd[:, iu[0]], vd[:, iu[1]]
+    feat = torch.cat([f[:, iu[0]], f[:, iu[1]], v1, v2, torch.norm(v1 - v2, dim=-1, keepdim=True)], dim=-1)
+    ref = torch.sigmoid(md.edge_mlp(feat.view(-1, feat.shape[-1]))).view(B, -1)
+    ref.backward(go.double())
+    assert idx == iu.t().tolist()
+    assert_close(probs, ref, 2e-5, "edge probs")
+    assert_close(vg.grad, vd.grad, 2e-4, "d vertices")
+    for k, p in md.named_parameters():
+        if k.startswith("spatial_proj"):
+            assert k not in got and p.grad is None          # unused in the reference as well (SURVEY Q3)
+            continue
+        assert_close(got[k], p.grad, 3e-4, f"grad {k}")
+
+
+def test_edge_predictor_unsupported_dims(ops):
+    from models.EdgePredictor import EdgePredictor
+    with pytest.raises(AssertionError):                      # nn.MultiheadAttention: embed_dim must be divisible by num_heads
+        EdgePredictor(hidden_dim=512, num_heads=7)
+    with pytest.raises(ops._lib.WfError):
+        EdgePredictor(vertex_dim=2)
+
+
 def test_gather_prefix_and_vertex_split(ops):
     torch.manual_seed(7)
     B, V = 4, 10

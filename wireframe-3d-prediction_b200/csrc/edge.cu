@@ -404,11 +404,17 @@ extern "C" int wf_attn_fwd(const float* qkv, const int32_t* v_off, const int64_t
                            int max_c, float* out, float* probs, const uint8_t* keep, float keep_scale, wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || max_c <= 0) return WF_OK;
-    WF_CHECK_ARG(head_dim == 64, "wf_attn_fwd: head_dim %d not built (64 only)", head_dim);
+    WF_CHECK_ARG(head_dim == 16 || head_dim == 32 || head_dim == 64 || head_dim == 128, "wf_attn_fwd: head_dim %d not built (16, 32, 64, 128)", head_dim);
     WF_CHECK_ARG(!((probs || keep) && !p_off), "wf_attn_fwd: probs/keep need p_off");
     size_t smem; int rc = attn_smem(max_c, head_dim, false, &smem); if (rc) return rc;
-    WF_CUDA(cudaFuncSetAttribute(edge::attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    edge::attn_fwd_kernel<64><<<B * heads, 256, smem, as_stream(stream)>>>(qkv, v_off, reinterpret_cast<const long long*>(p_off), heads, out, probs, keep, keep_scale);
+#define WF_ATTN_FWD(HD_)                                                                                                      \
+    case HD_:                                                                                                                 \
+        WF_CUDA(cudaFuncSetAttribute(edge::attn_fwd_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
+        edge::attn_fwd_kernel<HD_><<<B * heads, 256, smem, as_stream(stream)>>>(                                              \
+            qkv, v_off, reinterpret_cast<const long long*>(p_off), heads, out, probs, keep, keep_scale);                      \
+        break;
+    switch (head_dim) { WF_ATTN_FWD(16) WF_ATTN_FWD(32) WF_ATTN_FWD(64) WF_ATTN_FWD(128) }
+#undef WF_ATTN_FWD
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -417,11 +423,17 @@ extern "C" int wf_attn_bwd(const float* d_out, const float* qkv, const float* pr
                            wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || max_c <= 0) return WF_OK;
-    WF_CHECK_ARG(head_dim == 64, "wf_attn_bwd: head_dim %d not built (64 only)", head_dim);
+    WF_CHECK_ARG(head_dim == 16 || head_dim == 32 || head_dim == 64 || head_dim == 128, "wf_attn_bwd: head_dim %d not built (16, 32, 64, 128)", head_dim);
     WF_CHECK_ARG(probs && p_off, "wf_attn_bwd: needs saved probabilities");
     size_t smem; int rc = attn_smem(max_c, head_dim, true, &smem); if (rc) return rc;
-    WF_CUDA(cudaFuncSetAttribute(edge::attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    edge::attn_bwd_kernel<64><<<B * heads, 256, smem, as_stream(stream)>>>(d_out, qkv, probs, v_off, reinterpret_cast<const long long*>(p_off), heads, d_qkv, keep, keep_scale);
+#define WF_ATTN_BWD(HD_)                                                                                                      \
+    case HD_:                                                                                                                 \
+        WF_CUDA(cudaFuncSetAttribute(edge::attn_bwd_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
+        edge::attn_bwd_kernel<HD_><<<B * heads, 256, smem, as_stream(stream)>>>(                                              \
+            d_out, qkv, probs, v_off, reinterpret_cast<const long long*>(p_off), heads, d_qkv, keep, keep_scale);             \
+        break;
+    switch (head_dim) { WF_ATTN_BWD(16) WF_ATTN_BWD(32) WF_ATTN_BWD(64) WF_ATTN_BWD(128) }
+#undef WF_ATTN_BWD
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -441,8 +453,14 @@ extern "C" int wf_edge_pair_bwd(const float* dz1, const float* dist, const float
                                 wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || T <= 0) return WF_OK;
-    WF_CHECK_ARG(C == 512, "wf_edge_pair_bwd: C=%d not built (512 only)", C);
-    edge::edge_pair_bwd_kernel<16><<<T, 256, 0, as_stream(stream)>>>(dz1, dist, verts, wd, v_off, reinterpret_cast<const long long*>(e_off), B, dP, dQ, d_verts, d_wd);
+    WF_CHECK_ARG(C == 128 || C == 256 || C == 512 || C == 1024, "wf_edge_pair_bwd: C=%d not built (128, 256, 512, 1024)", C);
+#define WF_PAIR_BWD(CPL_)                                                                                                     \
+    case CPL_ * 32:                                                                                                           \
+        edge::edge_pair_bwd_kernel<CPL_><<<T, 256, 0, as_stream(stream)>>>(                                                   \
+            dz1, dist, verts, wd, v_off, reinterpret_cast<const long long*>(e_off), B, dP, dQ, d_verts, d_wd);                \
+        break;
+    switch (C) { WF_PAIR_BWD(4) WF_PAIR_BWD(8) WF_PAIR_BWD(16) WF_PAIR_BWD(32) }
+#undef WF_PAIR_BWD
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -451,9 +469,15 @@ extern "C" int wf_edge_out_fwd(const float* h, const float* w, const float* bias
                                float* probs, wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || max_e <= 0) return WF_OK;
-    WF_CHECK_ARG(K == 128, "wf_edge_out_fwd: K=%d not built (128 only)", K);
+    WF_CHECK_ARG(K == 32 || K == 64 || K == 128 || K == 256, "wf_edge_out_fwd: K=%d not built (32, 64, 128, 256)", K);
     const long long warps = (long long)B * max_e;
-    edge::edge_out_fwd_kernel<4><<<cdiv(warps * 32, 256), 256, 0, as_stream(stream)>>>(h, w, bias, reinterpret_cast<const long long*>(e_off), B, max_e, probs);
+#define WF_OUT_FWD(KPL_)                                                                                                      \
+    case KPL_ * 32:                                                                                                           \
+        edge::edge_out_fwd_kernel<KPL_><<<cdiv(warps * 32, 256), 256, 0, as_stream(stream)>>>(                                \
+            h, w, bias, reinterpret_cast<const long long*>(e_off), B, max_e, probs);                                          \
+        break;
+    switch (K) { WF_OUT_FWD(1) WF_OUT_FWD(2) WF_OUT_FWD(4) WF_OUT_FWD(8) }
+#undef WF_OUT_FWD
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -462,10 +486,16 @@ extern "C" int wf_edge_out_bwd(const float* d_probs, const float* probs, const f
                                int B, int K, int max_e, float* dh, float* dw, float* db, wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || max_e <= 0) return WF_OK;
-    WF_CHECK_ARG(K == 128, "wf_edge_out_bwd: K=%d not built (128 only)", K);
+    WF_CHECK_ARG(K == 32 || K == 64 || K == 128 || K == 256, "wf_edge_out_bwd: K=%d not built (32, 64, 128, 256)", K);
     const long long warps = (long long)B * max_e;
     const int grid = (int)(cdiv(warps * 32, 256) < sm_count() * 8 ? cdiv(warps * 32, 256) : sm_count() * 8);
-    edge::edge_out_bwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(d_probs, probs, h, w, reinterpret_cast<const long long*>(e_off), B, max_e, dh, dw, db);
+#define WF_OUT_BWD(KPL_)                                                                                                      \
+    case KPL_ * 32:                                                                                                           \
+        edge::edge_out_bwd_kernel<KPL_><<<grid, 256, 0, as_stream(stream)>>>(                                                 \
+            d_probs, probs, h, w, reinterpret_cast<const long long*>(e_off), B, max_e, dh, dw, db);                           \
+        break;
+    switch (K) { WF_OUT_BWD(1) WF_OUT_BWD(2) WF_OUT_BWD(4) WF_OUT_BWD(8) }
+#undef WF_OUT_BWD
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

@@ -35,8 +35,13 @@ class EdgePredictor(nn.Module):
             nn.Linear(hidden_dim // 2, hidden_dim // 4), nn.GELU(),
             nn.Linear(hidden_dim // 4, 1))
         self._dims = (vertex_dim, hidden_dim, num_heads)
-        if (vertex_dim, hidden_dim, num_heads) != (3, 512, 8):
-            raise NotImplementedError("EdgePredictor kernels are built for vertex_dim=3, hidden_dim=512, num_heads=8")
+        # nn.MultiheadAttention above has already raised the reference's AssertionError when num_heads does not divide
+        # hidden_dim.  The kernels are instantiated for hidden_dim in {128, 256, 512, 1024} (the pair layer keeps hidden_dim / 32
+        # channels per lane, the output layer hidden_dim / 128) and head widths 16 / 32 / 64 / 128; vertices are 3-D
+        # (PointCloudToWireframe.py:41 is the only constructor call in the reference: vertex_dim=3, defaults otherwise).
+        if vertex_dim != 3 or hidden_dim not in (128, 256, 512, 1024) or hidden_dim // num_heads not in (16, 32, 64, 128):
+            raise ops._lib.WfError(f"EdgePredictor(vertex_dim={vertex_dim}, hidden_dim={hidden_dim}, num_heads={num_heads}): kernels "
+                                   "exist for vertex_dim=3, hidden_dim in {128,256,512,1024}, hidden_dim/num_heads in {16,32,64,128}")
 
     def _get_edge_indices(self, num_vertices):
         return torch.tensor(pair_list(num_vertices), dtype=torch.long, device=next(self.parameters()).device)
@@ -46,7 +51,7 @@ class EdgePredictor(nn.Module):
 
     def forward_ragged(self, verts, rg):
         """verts: packed (T,3) vertices of all samples; rg: ops.Ragged.  Returns probs (B, max_e), zero padded."""
-        H = 512
+        H = self._dims[1]
         dev = verts.device
         vp, att, em = self.vertex_proj, self.attention, self.edge_mlp
         f = ops.linear_ln_act(verts, vp[0].weight, vp[0].bias, vp[1].weight, vp[1].bias, ACT_GELU)
@@ -55,11 +60,11 @@ class EdgePredictor(nn.Module):
         qkv = ops.linear_ln_act(f, att.in_proj_weight, att.in_proj_bias)
         p_att = att.dropout if self.training else 0.0
         ka, kas = ops.dropout_keep((rg.Ptot,), p_att, p_att > 0.0, dev)
-        o = ops.AttentionCore.apply(qkv, rg, ka, kas)
+        o = ops.AttentionCore.apply(qkv, rg, ka, kas, self._dims[2])
         f = ops.linear_ln_act(o, att.out_proj.weight, att.out_proj.bias, residual=f)       # reference :114
-        W1 = em[0].weight                                                                   # (512, 1031)
+        W1 = em[0].weight                                                                   # (H, 2H + 7): (512, 1031)
         # first edge layer on [f_i | f_j | v_i | v_j | dist] = P[i] + Q[j] + w*dist: both feature blocks in ONE product
-        # against the stacked, contiguous (1024, 512) weight (the 1031-wide rows are not 16-byte aligned for TMA)
+        # against the stacked, contiguous (2H, H) weight (the 2H + 7-wide rows are not 16-byte aligned for TMA)
         Wf = torch.cat([W1[:, :H], W1[:, H:2 * H]], dim=0)
         Wv = torch.cat([W1[:, 2 * H:2 * H + 3], W1[:, 2 * H + 3:2 * H + 6]], dim=0)
         PQ = ops.linear_ln_act(verts, Wv, residual=ops.linear_ln_act(f, Wf))               # (T, 1024)

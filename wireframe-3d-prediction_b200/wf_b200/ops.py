@@ -666,9 +666,13 @@ def _enc_mlp_backward(dh_top, hs, zs, means, rstds, layers, sms):
 
 
 INFER_CHUNK_ROWS = int(os.environ.get("WF_B200_INFER_CHUNK_ROWS", str(1 << 19)))
+# L2-resident form: chunks small enough that every N x C activation lives and dies in the 126 MB L2.  37 x 256 rows make the
+# 256 x 256 cluster tiles of the 1024 / 2048 / 512-wide layers 148 / 296 / 74 per chunk: whole waves of the 74 CTA pairs.
+INFER_L2 = os.environ.get("WF_B200_INFER_L2", "0") == "1"
+INFER_L2_ROWS = int(os.environ.get("WF_B200_INFER_L2_ROWS", str(37 * 256)))
 
 
-def encoder_pooled_infer(x, params, *, chunk_rows=None, index_offset=0, points_total=None, reduce_fn=None):
+def encoder_pooled_infer(x, params, *, chunk_rows=None, index_offset=0, points_total=None, reduce_fn=None, l2_resident=None):
     """Inference form of EncoderPointMLP_TC (no autograd, nothing saved): the per-point MLP runs over row chunks of at most
     `chunk_rows` points through three reused bf16 buffers, so a batch of million-point scans (BASELINE.json configs[3]:
     8 x 1M points = 139 GB of training activations) needs ~2.5 KB/point of the largest chunk instead.  The pools accumulate
@@ -687,6 +691,9 @@ def encoder_pooled_infer(x, params, *, chunk_rows=None, index_offset=0, points_t
     dev = x.device
     if N < _FUSED_MIN_POINTS:
         raise _lib.WfError(f"encoder_pooled_infer needs >= {_FUSED_MIN_POINTS} points per cloud (got {N})")
+    l2 = INFER_L2 if l2_resident is None else bool(l2_resident)
+    if l2 and chunk_rows is None:
+        chunk_rows = INFER_L2_ROWS
     chunk = INFER_CHUNK_ROWS if chunk_rows is None else int(chunk_rows)
     chunk = max(128, (min(chunk, M) + 127) // 128 * 128)
     # rows are processed in super-chunks (one set of activation buffers, 17.4 KB per row, reused); inside a super-chunk the
@@ -703,9 +710,21 @@ def encoder_pooled_infer(x, params, *, chunk_rows=None, index_offset=0, points_t
     C5, K5 = W5.shape
     rows = min(sup, M)
     bf = lambda c: torch.empty(rows, c, device=dev, dtype=torch.bfloat16)
-    h1 = bf(W1.shape[0])
-    zs = [bf(W.shape[0]) for (W, _, _, _) in layers]
-    hs = [bf(W.shape[0]) for (W, _, _, _) in layers]
+    if l2:
+        # two buffers, ping-pong: X (widest layer) holds h1, then z3 -> h3 in place; Y holds z2 -> h2, then z4 -> h4.  The
+        # footprint (rows x (Cmax + C2) x 2 B = 58 MB at 9472 rows) is rewritten chunk after chunk while still dirty in L2,
+        # so in steady state neither the GEMM stores nor the LayerNorm passes move DRAM bytes.
+        widths = [W.shape[0] for (W, _, _, _) in layers]
+        if not (len(widths) == 3 and widths[0] == widths[2] and W1.shape[0] <= widths[1]):
+            raise _lib.WfError("l2_resident: unexpected layer widths")
+        bx, by = bf(widths[1]), bf(widths[0])
+        h1 = bx.view(-1)[: rows * W1.shape[0]].view(rows, W1.shape[0])
+        zs = [by, bx, by]
+        hs = [by, bx, by]
+    else:
+        h1 = bf(W1.shape[0])
+        zs = [bf(W.shape[0]) for (W, _, _, _) in layers]
+        hs = [bf(W.shape[0]) for (W, _, _, _) in layers]
     means = [torch.empty(rows, device=dev, dtype=torch.float32) for _ in layers]
     rstds = [torch.empty(rows, device=dev, dtype=torch.float32) for _ in layers]
     part = torch.empty(call("wf_seg_part_floats", M, K5), device=dev, dtype=torch.float32)
@@ -987,17 +1006,18 @@ class GatherPrefix(torch.autograd.Function):
 
 
 class AttentionCore(torch.autograd.Function):
-    """softmax(q k^T / sqrt(d)) v for 8 heads, per sample -- the core of nn.MultiheadAttention
+    """softmax(q k^T / sqrt(d)) v for `heads` heads, per sample -- the core of nn.MultiheadAttention
     (models/EdgePredictor.py:109-111); in_proj / out_proj are LinearLNAct calls around it."""
 
     @staticmethod
-    def forward(ctx, qkv, rg: Ragged, keep, keep_scale):
+    def forward(ctx, qkv, rg: Ragged, keep, keep_scale, heads=8):
         _need_cuda(qkv)
         qkv = _f32c(qkv)
         E = qkv.shape[1] // 3
+        ctx.heads = heads = int(heads)
         out = torch.empty(rg.T, E, device=qkv.device, dtype=torch.float32)
         probs = torch.empty(rg.Ptot, device=qkv.device, dtype=torch.float32)
-        call("wf_attn_fwd", _p(qkv), _p(rg.v_off), _p(rg.p_off), rg.B, 8, E // 8, rg.max_c, _p(out), _p(probs), _p(keep),
+        call("wf_attn_fwd", _p(qkv), _p(rg.v_off), _p(rg.p_off), rg.B, heads, E // heads, rg.max_c, _p(out), _p(probs), _p(keep),
              float(keep_scale), _s())
         _count()
         ctx.save_for_backward(qkv, probs, keep)
@@ -1011,10 +1031,10 @@ class AttentionCore(torch.autograd.Function):
         E = qkv.shape[1] // 3
         d_qkv = torch.empty_like(qkv)
         d_out = _f32c(d_out)
-        call("wf_attn_bwd", _p(d_out), _p(qkv), _p(probs), _p(rg.v_off), _p(rg.p_off), rg.B, 8, E // 8, rg.max_c,
+        call("wf_attn_bwd", _p(d_out), _p(qkv), _p(probs), _p(rg.v_off), _p(rg.p_off), rg.B, ctx.heads, E // ctx.heads, rg.max_c,
              _p(d_qkv), _p(keep), float(ctx.keep_scale), _s())
         _count()
-        return d_qkv, None, None, None
+        return d_qkv, None, None, None, None
 
 
 class EdgePairLayer(torch.autograd.Function):
