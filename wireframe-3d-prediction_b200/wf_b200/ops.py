@@ -419,6 +419,12 @@ def side_ln_bwd(dh, z, mean, rstd, gamma, beta, dz, dgamma, dbeta, dbias, r0, r1
     return sg
 
 
+def _side_bytes(side) -> float:
+    """Algorithmic HBM bytes of the LayerNorm segments a GEMM launch carries: forward reads z and writes h (4 B / element),
+    backward reads dh and z and writes dz (6 B / element)."""
+    return float(sum(sg.rows * sg.C * (6 if sg.kind == _lib.SIDE_LN_BWD else 4) for sg in (side or ())))
+
+
 def _seg_array(side):
     side = [s for s in side if s.rows > 0]
     if len(side) > _lib.SIDE_MAX:
@@ -443,7 +449,7 @@ def gemm_bf16(A, B, *, M, N, K, kmajor=True, bias=None, out, accumulate=False, s
              _dt(out), int(accumulate), int(split_k), _p(rowstats), _s())
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K))
+        prof.append((e0, e1, 2.0 * M * N * K, _side_bytes(side)))
     _count()
     return out
 
@@ -461,7 +467,7 @@ def gemm_bf16_ownln(A, Wb, *, M, N, K, bias, z, rowstats, gamma, beta, h, mean, 
          _p(h), _p(mean), _p(rstd), 1e-5, _p(done), ctypes.byref(arr), n, _s())
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K))
+        prof.append((e0, e1, 2.0 * M * N * K, 4.0 * M * N + _side_bytes(side)))
     _count(2)
 
 
@@ -482,7 +488,7 @@ def gemm_bf16_pool(A, Wb, *, M, N, K, bias, points_per_cloud, row_offset, mask, 
              int(row_offset), int(index_offset), _p(mask), _p(packed[0]), _p(packed[1]), _s())
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K))
+        prof.append((e0, e1, 2.0 * M * N * K, _side_bytes(side)))
     _count()
 
 
