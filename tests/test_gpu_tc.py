@@ -164,13 +164,17 @@ def test_enc_l1_kernels_fp32_dtype(ops):
         assert_close(a, r, 5e-5, f"l1 bwd {n} (no dx: channel-stationary kernel)")
 
 
-@pytest.mark.parametrize("M,raw_intensity", [(1, False), (255, False), (257, True), (5003, True)])
-def test_enc_l1_channel_stationary_kernels(ops, M, raw_intensity):
-    """The production first-layer kernels (thread owns a channel pair, LayerNorm statistics from the 9x9 Cholesky factor of
-    the centred layer instead of a reduction over channels) against torch autograd in fp64, incl. un-normalised
-    intensity (~5e4) and point counts that are not multiples of the staging block / the 8-point group."""
+@pytest.mark.parametrize("variant", ["mma_ntl1", "mma_ntl2", "simt"])
+@pytest.mark.parametrize("M,raw_intensity", [(1, False), (255, False), (257, True), (5003, True), (70001, False)])
+def test_enc_l1_channel_stationary_kernels(ops, M, raw_intensity, variant, monkeypatch):
+    """The production first-layer kernels (LayerNorm statistics from the 9x9 Cholesky factor of the centred layer instead of a
+    reduction over channels) against torch autograd in fp64, incl. un-normalised intensity (~5e4) and point counts
+    that are not multiples of the staging block / the 8-point group / one block per CTA.  Variants of the bf16-gradient
+    backward: the SIMT kernel (l1c::bwd_kernel, the default) and the 3xTF32 mma.sync kernel with 8 or 16 points per barrier
+    (l1m::bwd_kernel<1|2>, WF_B200_L1_BWD=mma1|mma2; correct but slower on a B200, kept as the measured alternative)."""
     import torch.nn.functional as F
     from wf_b200._lib import call, F32, BF16
+    monkeypatch.setenv("WF_B200_L1_BWD", {"mma_ntl1": "mma1", "mma_ntl2": "mma2", "simt": "simt"}[variant])
     torch.manual_seed(M)
     x = torch.randn(M, 8, device="cuda")
     if raw_intensity:

@@ -619,6 +619,245 @@ fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// layer 1 backward (no dx) on the same tensor-core formulation, bf16 gradient in.  The channel-stationary SIMT kernel
+// (l1c::bwd_kernel) spends its time on shared-memory round trips (two staged-point reads per FMA group, row sums through a
+// per-thread partial array): 0.67 ms for 0.68 GB, 0.15 of the HBM roofline.  Here the layer is recomputed TRANSPOSED,
+//   z^T (16 channels x 8 points) = Wt (16 x 8) . x^T (8 x 8),          3xTF32 as in the forward,
+// so that the accumulator fragment of a thread -- channel rows (g, g+8) x points (2t, 2t+1) -- IS the A fragment of the
+// weight-gradient product dW (16 channels x 8 inputs) += dz^T (16 x 8 points) . x (8 points x 8 inputs): A wants columns
+// (t, t+4), and since the point index is summed over, reading x in the permuted order (2t, 2t+1) makes the two agree
+// with no data movement.  A warp owns 64 channels as 4 m-tiles whose rows are assigned so that a thread's 8 channels are
+// CONSECUTIVE (channel = 64 warp + 8 g + 2 j + half): its share of a point's gradient row is one 16-byte load, a warp
+// reads 4 points x 128 contiguous bytes per instruction, and channel pairs (2j, 2j+1) sit in (c0,c2)/(c1,c3) for the
+// packed f32x2 epilogue.  Steps of 16 points: phase 1 forms xhat, the masked gradient (kept as bf16 -- it is dh or 0) and
+// the two LayerNorm-backward row sums (in-thread over 8 channels, shuffles over the 8 row groups, one partial per warp
+// and point in shared memory, added in warp order: deterministic); ONE __syncthreads per step (the partial buffer is
+// double-buffered); phase 2 finishes dz, accumulates db / dgamma / dbeta per thread and dW by 3xTF32 MMAs.
+// ------------------------------------------------------------------------------------------
+constexpr int BPMAX = 16;                                 // points per step: 8 per n-tile, NTL n-tiles (1 or 2)
+
+struct SmemB {
+    l1c::Smem base;          // prologue scratch, Cholesky factor R, column means
+    float xh[PB][XS];        // staged points, TF32 "big" parts
+    float xl[PB][XS];        // TF32 "small" parts
+    float rs[PB];            // rstd per staged point (0 for rows beyond M)
+    float2 part[2][BPMAX][NT / 32];                          // [buffer][point of the step][warp] (sum gh, sum gh * xhat)
+    uint4 wh[NT / 32][4][32];                             // A fragments of the centred weights, TF32 big parts: [warp][m-tile][lane]
+    uint4 wl[NT / 32][4][32];                             // small parts
+    u64 bias2[NT / 32][4][8];                             // centred bias pairs: [warp][m-tile][row group]
+};
+
+// NTL = 2: 16 points per block-wide barrier, ~170 registers -> one CTA per SM;  NTL = 1: 8 points per barrier, two CTAs per SM
+template <int NTL>
+__global__ void __launch_bounds__(NT, NTL == 1 ? 2 : 1)
+bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ g,
+           const float* __restrict__ be, const __nv_bfloat16* __restrict__ dh, float* __restrict__ dW, float* __restrict__ db,
+           float* __restrict__ dg, float* __restrict__ dbe, int M, float eps) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SmemB& s = *reinterpret_cast<SmemB*>(smem_raw);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, gid = lane >> 2, tig = lane & 3;
+    {
+        u64 w2[D], b2;
+        l1c::prologue(s.base, W, b, w2, b2);
+    }
+    const int ch8 = warp * 64 + gid * 8;                  // this thread's 8 consecutive channels
+    // A fragments of the centred weights for the 4 m-tiles: rows (g, g+8) = channels (ch8 + 2j, ch8 + 2j + 1), columns (t, t+4)
+    // (kept in shared memory, fragment-major: two 16-byte loads per m-tile and n-tile instead of 32 registers)
+    u64 g2[4], be2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c0 = ch8 + 2 * j, c1 = c0 + 1;
+        const float wv[4] = {W[(size_t)c0 * D + tig] - s.base.cm[tig], W[(size_t)c1 * D + tig] - s.base.cm[tig],
+                             W[(size_t)c0 * D + tig + 4] - s.base.cm[tig + 4], W[(size_t)c1 * D + tig + 4] - s.base.cm[tig + 4]};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float hi = tf32_rn(wv[q]);
+            ah[q] = __float_as_uint(hi); al[q] = __float_as_uint(tf32_rn(wv[q] - hi));
+        }
+        s.wh[warp][j][lane] = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+        s.wl[warp][j][lane] = make_uint4(al[0], al[1], al[2], al[3]);
+        if (tig == 0) s.bias2[warp][j][gid] = l1c::pk2(b[c0] - s.base.cm[8], b[c1] - s.base.cm[8]);
+        g2[j] = l1c::pk2(g[c0], g[c1]); be2[j] = l1c::pk2(be[c0], be[c1]);
+    }
+    float aW[4][4];                                       // dW accumulators: channels (c0, c0, c1, c1) x inputs (2t, 2t+1, 2t, 2t+1)
+    u64 adb[4], adg[4], adbe[4];                          // per channel pair, over this thread's points only
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        adb[j] = adg[j] = adbe[j] = 0ull;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aW[j][q] = 0.f;
+    }
+    constexpr int BP = 8 * NTL;
+    const int nblk = (M + PB - 1) / PB;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    // gradient words of one step: [n-tile][point 2t / 2t+1] -> 8 bf16 of this thread's channels
+    uint4 cur[NTL][2], nxt[NTL][2];
+    auto load_step = [&](uint4 (&dst)[NTL][2], int pbase, int npts_left) {       // pbase: global index of the step's first point
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int q = nt * 8 + 2 * tig + e;
+                dst[nt][e] = q < npts_left ? *reinterpret_cast<const uint4*>(dh + (size_t)(pbase + q) * C + ch8) : zero4;
+            }
+    };
+    float4 xa = make_float4(0, 0, 0, 0), xb = xa;
+    int blk = blockIdx.x;
+    if (blk < nblk) {
+        if (blk * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(blk * PB + t) * D); xa = src[0]; xb = src[1]; }
+        load_step(cur, blk * PB, min(PB, M - blk * PB));
+    }
+    int buf = 0;
+    for (; blk < nblk; blk += gridDim.x) {
+        const int p0 = blk * PB;
+        __syncthreads();                                  // previous block's readers are done with the staging buffers
+        {
+            const float xv[9] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, 1.0f};
+            float var = 0.f;
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = i; j < 9; ++j) a = fmaf(s.base.R[q++], xv[j], a);
+                var = fmaf(a, a, var);
+            }
+            s.rs[t] = p0 + t < M ? rsqrtf(var + eps) : 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { const float hi = tf32_rn(xv[k]); s.xh[t][k] = hi; s.xl[t][k] = tf32_rn(xv[k] - hi); }
+        }
+        const int nb = blk + gridDim.x;
+        if (nb < nblk && nb * PB + t < M) { const float4* src = reinterpret_cast<const float4*>(x + (size_t)(nb * PB + t) * D); xa = src[0]; xb = src[1]; }
+        __syncthreads();
+        const int np = min(PB, M - p0);
+        for (int q0 = 0; q0 < np; q0 += BP) {
+            // the next step's gradient words are requested now and consumed one step later (also across staging blocks)
+            if (q0 + BP < np) load_step(nxt, p0 + q0 + BP, np - q0 - BP);
+            else if (nb < nblk) load_step(nxt, nb * PB, min(PB, M - nb * PB));
+            u64 xhat[NTL][4][2];                            // [n-tile][m-tile][point e]: (channel c0, channel c1)
+            // ---- phase 1: recompute, mask, row sums
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+                const int pr = q0 + nt * 8 + gid;         // B fragment: column n = g -> staged point, rows k = t, t+4
+                const uint32_t bh0 = __float_as_uint(s.xh[pr][tig]), bh1 = __float_as_uint(s.xh[pr][tig + 4]);
+                const uint32_t bl0 = __float_as_uint(s.xl[pr][tig]), bl1 = __float_as_uint(s.xl[pr][tig + 4]);
+                const int pa = q0 + nt * 8 + 2 * tig;     // accumulator columns: staged points pa, pa + 1
+                const float rsa = s.rs[pa], rsb = s.rs[pa + 1];
+                const u64 rsa2 = l1c::pk2(rsa, rsa), rsb2 = l1c::pk2(rsb, rsb);
+                u64 s1a = 0ull, s2a = 0ull, s1b = 0ull, s2b = 0ull;
+                uint32_t wa[4] = {cur[nt][0].x, cur[nt][0].y, cur[nt][0].z, cur[nt][0].w};
+                uint32_t wb[4] = {cur[nt][1].x, cur[nt][1].y, cur[nt][1].z, cur[nt][1].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float d[4];
+                    l1c::up2(s.bias2[warp][j][gid], d[0], d[2]); d[1] = d[0]; d[3] = d[2];
+                    {
+                        const uint4 fh = s.wh[warp][j][lane], fl = s.wl[warp][j][lane];
+                        const uint32_t ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
+                        mma_tf32(d, al, bh0, bh1);
+                        mma_tf32(d, ah, bl0, bl1);
+                        mma_tf32(d, ah, bh0, bh1);
+                    }
+                    const u64 xa2 = l1c::mul2(l1c::pk2(d[0], d[2]), rsa2), xb2 = l1c::mul2(l1c::pk2(d[1], d[3]), rsb2);
+                    float y0, y1, y2, y3;
+                    l1c::up2(l1c::fma2(xa2, g2[j], be2[j]), y0, y1);
+                    l1c::up2(l1c::fma2(xb2, g2[j], be2[j]), y2, y3);
+                    wa[j] &= (y0 > 0.f ? 0x0000FFFFu : 0u) | (y1 > 0.f ? 0xFFFF0000u : 0u);        // g = dh * [y > 0]
+                    wb[j] &= (y2 > 0.f ? 0x0000FFFFu : 0u) | (y3 > 0.f ? 0xFFFF0000u : 0u);
+                    const u64 gha = l1c::mul2(lnb::bf2(wa[j]), g2[j]), ghb = l1c::mul2(lnb::bf2(wb[j]), g2[j]);
+                    s1a = l1c::add2(s1a, gha); s2a = l1c::fma2(gha, xa2, s2a);
+                    s1b = l1c::add2(s1b, ghb); s2b = l1c::fma2(ghb, xb2, s2b);
+                    xhat[nt][j][0] = xa2; xhat[nt][j][1] = xb2;
+                }
+                cur[nt][0] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                cur[nt][1] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                float v[4], lo, hi;
+                l1c::up2(s1a, lo, hi); v[0] = lo + hi; l1c::up2(s2a, lo, hi); v[1] = lo + hi;
+                l1c::up2(s1b, lo, hi); v[2] = lo + hi; l1c::up2(s2b, lo, hi); v[3] = lo + hi;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 4);
+                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+                }
+                if (gid == 0) {
+                    s.part[buf][nt * 8 + 2 * tig][warp] = make_float2(v[0], v[1]);
+                    s.part[buf][nt * 8 + 2 * tig + 1][warp] = make_float2(v[2], v[3]);
+                }
+            }
+            __syncthreads();
+            // ---- phase 2: dz, parameter gradients
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+                const int pa = q0 + nt * 8 + 2 * tig;
+                float c1a = 0.f, c2a = 0.f, c1b = 0.f, c2b = 0.f;
+                {
+                    const float4* pp = reinterpret_cast<const float4*>(&s.part[buf][nt * 8 + 2 * tig][0]);      // 2 points x 8 warps x (s1, s2)
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) { const float4 u = pp[w4]; c1a += u.x; c2a += u.y; c1a += u.z; c2a += u.w; }
+#pragma unroll
+                    for (int w4 = 4; w4 < 8; ++w4) { const float4 u = pp[w4]; c1b += u.x; c2b += u.y; c1b += u.z; c2b += u.w; }
+                }
+                const float rsa = s.rs[pa], rsb = s.rs[pa + 1];
+                const u64 rsa2 = l1c::pk2(rsa, rsa), rsb2 = l1c::pk2(rsb, rsb);
+                const u64 n1a = l1c::pk2(-c1a * (1.0f / C), -c1a * (1.0f / C)), n2a = l1c::pk2(-c2a * (1.0f / C), -c2a * (1.0f / C));
+                const u64 n1b = l1c::pk2(-c1b * (1.0f / C), -c1b * (1.0f / C)), n2b = l1c::pk2(-c2b * (1.0f / C), -c2b * (1.0f / C));
+                // B fragment of the weight-gradient product: rows k = (t, t+4) <-> points (pa, pa+1), column n = g = input feature
+                const uint32_t xh0 = __float_as_uint(s.xh[pa][gid]), xh1 = __float_as_uint(s.xh[pa + 1][gid]);
+                const uint32_t xl0 = __float_as_uint(s.xl[pa][gid]), xl1 = __float_as_uint(s.xl[pa + 1][gid]);
+                const uint32_t wa[4] = {cur[nt][0].x, cur[nt][0].y, cur[nt][0].z, cur[nt][0].w};
+                const uint32_t wb[4] = {cur[nt][1].x, cur[nt][1].y, cur[nt][1].z, cur[nt][1].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const u64 gya = lnb::bf2(wa[j]), gyb = lnb::bf2(wb[j]);
+                    const u64 xa2 = xhat[nt][j][0], xb2 = xhat[nt][j][1];
+                    // dz = rstd * (g * gamma - c1 - xhat * c2)
+                    const u64 dza = l1c::mul2(rsa2, l1c::add2(l1c::fma2(xa2, n2a, l1c::mul2(gya, g2[j])), n1a));
+                    const u64 dzb = l1c::mul2(rsb2, l1c::add2(l1c::fma2(xb2, n2b, l1c::mul2(gyb, g2[j])), n1b));
+                    adb[j] = l1c::add2(adb[j], l1c::add2(dza, dzb));
+                    adg[j] = l1c::fma2(gya, xa2, l1c::fma2(gyb, xb2, adg[j]));
+                    adbe[j] = l1c::add2(adbe[j], l1c::add2(gya, gyb));
+                    float e[4];                            // A fragment order: (c0, pa), (c1, pa), (c0, pa+1), (c1, pa+1)
+                    l1c::up2(dza, e[0], e[1]); l1c::up2(dzb, e[2], e[3]);
+                    uint32_t eh[4], el[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float hi = tf32_rn(e[q]);
+                        eh[q] = __float_as_uint(hi); el[q] = __float_as_uint(tf32_rn(e[q] - hi));
+                    }
+                    mma_tf32(aW[j], el, xh0, xh1);
+                    mma_tf32(aW[j], eh, xl0, xl1);
+                    mma_tf32(aW[j], eh, xh0, xh1);
+                }
+            }
+            buf ^= 1;
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) { cur[nt][0] = nxt[nt][0]; cur[nt][1] = nxt[nt][1]; }
+        }
+    }
+    // dW: the MMA has already summed over the step's points; one atomic per entry per warp-owner thread
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c0 = ch8 + 2 * j, c1 = c0 + 1;
+        atomicAdd(dW + (size_t)c0 * D + 2 * tig, aW[j][0]); atomicAdd(dW + (size_t)c0 * D + 2 * tig + 1, aW[j][1]);
+        atomicAdd(dW + (size_t)c1 * D + 2 * tig, aW[j][2]); atomicAdd(dW + (size_t)c1 * D + 2 * tig + 1, aW[j][3]);
+        float v[6];
+        l1c::up2(adb[j], v[0], v[1]); l1c::up2(adg[j], v[2], v[3]); l1c::up2(adbe[j], v[4], v[5]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {                     // the four point-column lanes of a row group
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 1);
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 2);
+        }
+        if (tig == 0) {
+            atomicAdd(db + c0, v[0]); atomicAdd(db + c1, v[1]);
+            atomicAdd(dg + c0, v[2]); atomicAdd(dg + c1, v[3]);
+            atomicAdd(dbe + c0, v[4]); atomicAdd(dbe + c1, v[5]);
+        }
+    }
+}
+
 }  // namespace l1m
 
 __global__ void stats_finalize_kernel(const float2* __restrict__ st, int M, int parts, float invC, float eps,
@@ -783,7 +1022,8 @@ extern "C" int wf_enc_l1_fwd(const float* x, const float* W, const float* b, con
     WF_CHECK_ARG((reinterpret_cast<uintptr_t>(W) & 15) == 0, "wf_enc_l1_fwd: W must be 16-byte aligned");
     const int grid = min(cdiv(M, enc::l1c::PB), sm_count() * 2);
     // WF_B200_L1_MMA=0 selects the channel-stationary SIMT forward instead of the 3xTF32 tensor-core one
-    static const bool l1_mma = [] { const char* e = getenv("WF_B200_L1_MMA"); return !(e && e[0] == '0'); }();
+    const char* e_mma = getenv("WF_B200_L1_MMA");           // read per call: the tests flip it
+    const bool l1_mma = !(e_mma && e_mma[0] == '0');
     if (l1_mma && (h_dtype == WF_BF16 || h_dtype == WF_F32)) {
         if (h_dtype == WF_BF16) enc::l1m::fwd_kernel<WF_BF16><<<grid, enc::l1m::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
         else enc::l1m::fwd_kernel<WF_F32><<<grid, enc::l1m::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, h, M, eps);
@@ -804,8 +1044,30 @@ extern "C" int wf_enc_l1_bwd(const float* x, const float* W, const float* b, con
     if (M <= 0) return WF_OK;
     WF_CHECK_ARG(D == 8 && C == 512, "wf_enc_l1_bwd: built for D=8, C=512 (got D=%d C=%d)", D, C);
     WF_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, "wf_enc_l1_bwd: x, W must be 16-byte aligned");
-    if (dx == nullptr) {                                   // training: no input gradient -> channel-stationary kernel
+    if (dx == nullptr) {                                   // training: no input gradient
         const int g2 = min(cdiv(M, enc::l1c::PB), sm_count() * 2);
+        // WF_B200_L1_BWD=mma1|mma2 selects the 3xTF32 mma.sync kernel (8 / 16 points per barrier) for a bf16 gradient.  Measured
+        // on a B200 at 640,000 points: 0.97 / 0.76 ms against 0.67 ms for the channel-stationary SIMT kernel -- legacy
+        // mma.sync.m16n8k8.tf32 retires about one instruction per 6 clocks per SM here (the forward kernel shows the same
+        // rate), and the backward needs 6 of them per 16 x 8 tile -- so the SIMT kernel stays the default (read per call: the
+        // tests flip it)
+        const char* e_bwd = getenv("WF_B200_L1_BWD");
+        const bool l1_mma = e_bwd && e_bwd[0] == 'm';
+        if (l1_mma && dh_dtype == WF_BF16 && (reinterpret_cast<uintptr_t>(dh) & 15) == 0) {
+            const int ntl = e_bwd[3] == '2' ? 2 : 1;
+            const auto* dhb = static_cast<const __nv_bfloat16*>(dh);
+            const int smem = (int)sizeof(enc::l1m::SmemB);
+            if (ntl == 2) {
+                WF_CUDA(cudaFuncSetAttribute(enc::l1m::bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                enc::l1m::bwd_kernel<2><<<min(cdiv(M, enc::l1c::PB), sm_count()), enc::l1m::NT, smem, as_stream(stream)>>>(
+                    x, W, b, gamma, beta, dhb, dW, db, dgamma, dbeta, M, eps);
+            } else {
+                WF_CUDA(cudaFuncSetAttribute(enc::l1m::bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                enc::l1m::bwd_kernel<1><<<g2, enc::l1m::NT, smem, as_stream(stream)>>>(x, W, b, gamma, beta, dhb, dW, db, dgamma, dbeta, M, eps);
+            }
+            WF_LAUNCH_CHECK();
+            return WF_OK;
+        }
         if (dh_dtype == WF_BF16) enc::l1c::bwd_kernel<WF_BF16><<<g2, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, dh, dW, db, dgamma, dbeta, M, eps);
         else if (dh_dtype == WF_F32) enc::l1c::bwd_kernel<WF_F32><<<g2, enc::l1c::NT, 0, as_stream(stream)>>>(x, W, b, gamma, beta, dh, dW, db, dgamma, dbeta, M, eps);
         else { set_error("wf_enc_l1_bwd: bad dtype"); return WF_EINVAL; }

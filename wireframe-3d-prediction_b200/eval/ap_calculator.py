@@ -119,7 +119,7 @@ class APCalculator(object):
     def reset(self):
         self.ap_dict = {'tp_corners': 0, 'tp_fp_corners': 0, 'tp_fn_corners': 0, 'distance': 0, 'tp_edges': 0,
                         'wed': 0, 'tp_fp_edges': 0, 'tp_fn_edges': 0, 'average_corner_offset': 0,
-                        'corners_precision': 0, 'corners_recall': 0, 'corners_f1': 0, 'edges_precision': 0,
+                        'corners_precision': 0, 'corners_recall': 0, 'corner_f1': 0, 'edges_precision': 0,   # 'corner_f1': the reference's key (ap_calculator.py:119), never updated; 'corners_f1' appears in output_accuracy
                         'edges_recall': 0, 'edges_f1': 0}
 
     # ------------------------------------------------------------------------------------------------
