@@ -87,6 +87,19 @@ int wf_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const 
                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
                 wf_stream_t stream);
 
+/* Small-batch products of the 64-row heads (models/PointNetEncoder.py:57-65,115-116; models/VertexPredictor.py:94-117), TF32
+ * operands / fp32 accumulate, shaped for weight streaming (csrc/rowmlp.cu).  All dimensions and leading dimensions multiples of
+ * 4 floats, pointers 16-byte aligned.
+ *   wf_rowmlp_linear: Y[M,N] = X[M,K] * Wop^T (+ bias[N]).  trans_w = 0: W is [N,K] (nn.Linear forward);  trans_w = 1: W is
+ *     [K,N] read in place (dX = dZ * W of an nn.Linear whose weight is W).  A cluster of 8 CTAs per 64-column slab splits K and
+ *     adds the partial tiles over distributed shared memory in rank order: deterministic, no workspace.
+ *   wf_rowmlp_dw: dW[Nr,Kc] = dZ[Mb,Nr]^T * X[Mb,Kc] for Mb <= 128 batch rows (the reduction dimension), every entry written
+ *     once (no atomics, no zero fill); db[Nr] = column sums of dZ (exact fp32) when db != NULL. */
+int wf_rowmlp_linear(const float* X, int ldx, const float* W, int ldw, int trans_w, const float* bias, int M, int N, int K,
+                     float* Y, int ldy, wf_stream_t stream);
+int wf_rowmlp_dw(const float* dZ, int ldz, const float* X, int ldx, int Mb, int Nr, int Kc, float* dW, int ldw, float* db,
+                 wf_stream_t stream);
+
 /* out = dropout(act(LayerNorm(z))) + residual  -- one fused pass per row.
  * models/PointNetEncoder.py:37-40,58-63; models/VertexPredictor.py:28-54,110,114;
  * models/EdgePredictor.py:31-38,57-66.  gamma==NULL skips the normalisation (pure activation,

@@ -202,6 +202,69 @@ def test_enc_l1_channel_stationary_kernels(ops, M, raw_intensity, variant, monke
             assert_close(a, r, tol, f"l1 bwd {n} dtype {dt} M={M}")
 
 
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) to 10 mantissa bits."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 2048, 4096), (64, 4096, 512), (64, 256, 1024), (3, 512, 1024), (128, 1024, 512),
+                                   (100, 48, 1024), (64, 2048, 520), (1, 1024, 2048), (130, 512, 1024)])
+def test_rowmlp_kernels(ops, M, N, K):
+    """csrc/rowmlp.cu (the 64-row heads' weight-streaming products): forward Y = X W^T + b, dX = dZ W (W read in place) and
+    dW = dZ^T X (+ db) against float64 products of the TF32-rounded operands (the kernels round once with cvt.rna and
+    accumulate in fp32: 2e-5), against the unrounded float64 product at TF32 level (2e-3), and bit-reproducible."""
+    from wf_b200._lib import call
+    torch.manual_seed(M * 7 + N + K)
+    X = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
+    dZ = torch.randn(M, N, device="cuda")
+    Xr, Wr, dZr = _tf32_rna(X).double(), _tf32_rna(W).double(), _tf32_rna(dZ).double()
+    p, s = ops._p, ops._s
+    Y = torch.full((M, N), float("nan"), device="cuda")
+    call("wf_rowmlp_linear", p(X), K, p(W), K, 0, p(b), M, N, K, p(Y), N, s())
+    assert_close(Y, Xr @ Wr.t() + b.double(), 2e-5, "forward vs rounded operands")
+    assert_close(Y, X.double() @ W.double().t() + b.double(), 2e-3, "forward vs exact")
+    Y2 = torch.empty_like(Y)
+    call("wf_rowmlp_linear", p(X), K, p(W), K, 0, p(b), M, N, K, p(Y2), N, s())
+    assert torch.equal(Y, Y2), "forward not reproducible"
+    dX = torch.full((M, K), float("nan"), device="cuda")
+    call("wf_rowmlp_linear", p(dZ), N, p(W), K, 1, None, M, K, N, p(dX), K, s())
+    assert_close(dX, dZr @ Wr, 2e-5, "dX vs rounded operands")
+    assert_close(dX, dZ.double() @ W.double(), 2e-3, "dX vs exact")
+    if M <= 128:
+        dW = torch.full((N, K), float("nan"), device="cuda"); db = torch.full((N,), float("nan"), device="cuda")
+        call("wf_rowmlp_dw", p(dZ), N, p(X), K, M, N, K, p(dW), K, p(db), s())
+        assert_close(dW, dZr.t() @ Xr, 2e-5, "dW vs rounded operands")
+        assert_close(dW, dZ.double().t() @ X.double(), 2e-3, "dW vs exact")
+        assert_close(db, dZ.double().sum(0), 1e-6, "db")
+        dW2 = torch.empty_like(dW)
+        call("wf_rowmlp_dw", p(dZ), N, p(X), K, M, N, K, p(dW2), K, None, s())
+        assert torch.equal(dW, dW2), "dW not reproducible"
+
+
+def test_heads_route_through_rowmlp_and_match_the_tf32_path(ops):
+    """ops.linear_ln_act at 64 rows in the production precision: the rowmlp kernels (default) against the split-K kind::tf32
+    launches they replace (WF_B200_ROWMLP=0 behaviour, ops.USE_ROWMLP) -- same precision class, forward and all gradients."""
+    torch.manual_seed(11)
+    x = torch.randn(64, 1024, device="cuda"); W = torch.randn(2048, 1024, device="cuda") / 32; b = 0.1 * torch.randn(2048, device="cuda")
+    g = 1 + 0.1 * torch.randn(2048, device="cuda"); be = 0.1 * torch.randn(2048, device="cuda"); go = torch.randn(64, 2048, device="cuda")
+    res = {}
+    old = ops.USE_ROWMLP
+    try:
+        for flag in (True, False):
+            ops.USE_ROWMLP = flag
+            leaves = [t.clone().requires_grad_(True) for t in (x, W, b, g, be)]
+            n0 = ops.LAUNCHES
+            out = ops.linear_ln_act(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], 1)
+            out.backward(go)
+            res[flag] = (out.detach(), [t.grad for t in leaves], ops.LAUNCHES - n0)
+    finally:
+        ops.USE_ROWMLP = old
+    assert res[True][2] < res[False][2], "the rowmlp route should need fewer launches"
+    assert_close(res[True][0], res[False][0], 2e-3, "forward")
+    for n, a, r in zip("x W b gamma beta".split(), res[True][1], res[False][1]):
+        assert_close(a, r, 3e-3, f"grad {n}")
+
+
 @pytest.mark.parametrize("C", [512, 1024, 2048])
 def test_ln_relu_bf16_kernels(ops, C):
     """wf_ln_relu_bf16_fwd/bwd against torch autograd (fp64) on the same bf16-rounded inputs and the same row statistics."""
@@ -492,9 +555,11 @@ def test_encoder_point_sharded_matches_unsharded(ops):
 
 
 @pytest.mark.parametrize("M,N,K,tB", [(64, 2048, 4096, True), (64, 512, 4096, False), (64, 4096, 512, True), (100, 1024, 2048, True)])
-def test_tf32_split_k_forward_is_deterministic(ops, M, N, K, tB):
-    """Few-tile TF32 products (the 64-row heads) split the reduction over K; forward/dX products must stay bit-reproducible:
-    partial tiles go to workspace slices that are added in a fixed order (wf_gemm_tf32_splitk)."""
+def test_tf32_split_k_forward_is_deterministic(ops, M, N, K, tB, monkeypatch):
+    """Few-tile TF32 products split the reduction over K; forward/dX products must stay bit-reproducible: partial tiles go to
+    workspace slices that are added in a fixed order (wf_gemm_tf32_splitk).  Products with <= 128 rows take the rowmlp kernels
+    by default (test_rowmlp_kernels); this test pins the kind::tf32 route, which keeps serving taller few-tile products."""
+    monkeypatch.setattr(ops, "USE_ROWMLP", False)
     torch.manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda")
     B = torch.randn(N, K, device="cuda") / math.sqrt(K) if tB else torch.randn(K, N, device="cuda") / math.sqrt(K)

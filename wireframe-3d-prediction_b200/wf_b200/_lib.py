@@ -41,6 +41,8 @@ SIGNATURES = {
     "wf_gemm_bf16": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, I, P, P],
     "wf_gemm_tf32": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, P],
     "wf_gemm_tf32_splitk": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, P, L, P],
+    "wf_rowmlp_linear": [P, I, P, I, I, P, I, I, I, P, I, P],
+    "wf_rowmlp_dw": [P, I, P, I, I, I, I, P, I, P, P],
     "wf_gemm_bf16_side": [P, I, I, P, I, I, I, I, I, P, P, I, I, I, I, P, I, I, I, P, P, P, P, I, P],
     "wf_gemm_bf16_ownln": [P, I, P, I, I, I, I, P, P, P, P, P, P, P, P, F, P, P, I, P],
     "wf_ln_relu_bf16_fwd": [P, P, P, P, P, P, I, I, P],

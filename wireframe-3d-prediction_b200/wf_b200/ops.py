@@ -150,6 +150,9 @@ def _rowmajor(t: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 USE_TF32_HEADS = os.environ.get("WF_B200_TF32_HEADS", "1") == "1"
 _TC_MIN_MACS = 1 << 22
+USE_ROWMLP = os.environ.get("WF_B200_ROWMLP", "1") == "1"      # 0: the 64-row heads go back to the split-K kind::tf32 launches
+_ROWMLP_MAX_ROWS = 128
+_ROWMLP_MIN_WEIGHTS = 1 << 16
 
 
 def _tc_operand_ok(t: torch.Tensor) -> bool:
@@ -168,6 +171,22 @@ def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0,
     kb = B.shape[1] if transB else B.shape[0]
     if kb != K:
         raise ValueError(f"gemm shape mismatch {tuple(A.shape)} {tuple(B.shape)} tA={transA} tB={transB}")
+    if (tc and _PRECISION == "bf16" and USE_TF32_HEADS and USE_ROWMLP and alpha == 1.0 and beta == 0.0 and out is None
+            and _tc_operand_ok(A) and _tc_operand_ok(B) and (bias is None or bias.data_ptr() % 16 == 0)):
+        # the 64-row heads (csrc/rowmlp.cu): weight-streaming kernels instead of split-K tensor-core launches
+        rows = A.shape[0]                      # batch rows in every orientation (A is x, dz or dz)
+        if rows <= _ROWMLP_MAX_ROWS:
+            if transA and not transB and bias is None and M % 4 == 0 and N % 4 == 0 and M * N >= _ROWMLP_MIN_WEIGHTS:
+                out = torch.empty(M, N, device=A.device, dtype=torch.float32)        # dW[Nr, Kc] = A^T B, reduction over the rows
+                call("wf_rowmlp_dw", _p(A), A.stride(0), _p(B), B.stride(0), rows, M, N, _p(out), out.stride(0), None, _s())
+                _count()
+                return out
+            if not transA and N % 4 == 0 and K % 4 == 0 and N * K >= _ROWMLP_MIN_WEIGHTS:
+                out = torch.empty(M, N, device=A.device, dtype=torch.float32)        # forward (W [N,K]) or dX (W [K,N], read in place)
+                call("wf_rowmlp_linear", _p(A), A.stride(0), _p(B), B.stride(0), int(not transB), _p(bias), M, N, K, _p(out),
+                     out.stride(0), _s())
+                _count()
+                return out
     if (tc and _PRECISION == "bf16" and USE_TF32_HEADS and alpha == 1.0 and beta in (0.0, 1.0) and M * N * K >= _TC_MIN_MACS
             and _tc_operand_ok(A) and _tc_operand_ok(B) and (out is None or _tc_operand_ok(out))
             and (bias is None or bias.data_ptr() % 16 == 0)):
