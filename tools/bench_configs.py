@@ -117,16 +117,16 @@ def config4(quick):
             bl = B // world
             x, _, _ = make_inputs(seed=rank, B=bl, N=min(N, 100000), V=64)
             if N > 100000:                                   # tile the 100k synthetic cloud (host RNG time, not the bench)
-                x = x.repeat(1, N // 100000, 1)
+                x = x.repeat(1, -(-N // 100000), 1)[:, :N].contiguous()
             x = x.cuda()
             with torch.no_grad():
-                ms = timeit(lambda: enc.pooled(x), 2 if N >= 500000 else 4, warm=1)
+                ms = timeit(lambda: enc.pooled(x), max(2, min(20, int(4e6 // (bl * N)))), warm=2)
             mode, pts = f"batch-sharded {bl} clouds/GPU", bl * N * world
         else:                                                # fewer clouds than ranks: shard the points
             n = N // world
             x, _, _ = make_inputs(seed=0, B=B, N=min(N, 100000), V=64)
-            x = x.repeat(1, max(1, N // 100000), 1)[:, rank * n:(rank + 1) * n].contiguous().cuda()
-            ms = timeit(lambda: encode_point_sharded(enc, x, rank, world), 2, warm=1)
+            x = x.repeat(1, -(-N // 100000), 1)[:, rank * n:(rank + 1) * n].contiguous().cuda()
+            ms = timeit(lambda: encode_point_sharded(enc, x, rank, world), max(2, min(20, int(4e6 // (B * n)))), warm=2)
             mode, pts = f"point-sharded {n} points/GPU", B * N
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)

@@ -12,25 +12,43 @@
 namespace wf {
 namespace enc {
 
-// models/PointNetEncoder.py:85-86
-__global__ void point_mask_kernel(const float* __restrict__ x, int N, int D, uint8_t* __restrict__ mask,
-                                  float* __restrict__ valid) {
-    const int b = blockIdx.x;
+// models/PointNetEncoder.py:85-86.  Grid (slabs of PM_SLAB points, clouds): a single CTA per cloud walked a million-point scan
+// alone (1.6 ms for 32 MB).  The per-cloud count is accumulated as a float: sums of 0/1 stay exact below 2^24 points per cloud
+// whatever the order of the atomics (larger clouds take one slab per cloud, i.e. the serial order).
+constexpr int PM_SLAB = 2048;
+
+__global__ void __launch_bounds__(256)
+point_mask_kernel(const float* __restrict__ x, int N, int D, int slab, uint8_t* __restrict__ mask, float* __restrict__ valid) {
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * slab, n1 = min(N, n0 + slab);
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     int local = 0;
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const bool vec = D == 8 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    for (int n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
         const float* p = x + ((size_t)b * N + n) * D;
         float s = 0.f;
-        for (int d = 0; d < D; ++d) s += fabsf(p[d]);
+        if (vec) {
+            const float4 u = reinterpret_cast<const float4*>(p)[0], v = reinterpret_cast<const float4*>(p)[1];
+            s += fabsf(u.x); s += fabsf(u.y); s += fabsf(u.z); s += fabsf(u.w);       // same order as the scalar loop
+            s += fabsf(v.x); s += fabsf(v.y); s += fabsf(v.z); s += fabsf(v.w);
+        } else {
+            for (int d = 0; d < D; ++d) s += fabsf(p[d]);
+        }
         const int m = s > 1e-9f;
         mask[(size_t)b * N + n] = (uint8_t)m;
         local += m;
     }
-    atomicAdd(&cnt, local);
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt, local);
     __syncthreads();
-    if (threadIdx.x == 0) valid[b] = (float)max(cnt, 1);
+    if (threadIdx.x == 0 && cnt) atomicAdd(valid + b, (float)cnt);
+}
+
+__global__ void clamp_valid_kernel(float* __restrict__ valid, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) valid[b] = fmaxf(valid[b], 1.0f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1008,7 +1026,13 @@ pool_bwd_bf16_kernel(const float* __restrict__ g_max_m, const float* __restrict_
 extern "C" int wf_point_mask(const float* x, int B, int N, int D, uint8_t* mask, float* valid, wf_stream_t stream) {
     using namespace wf;
     if (B <= 0) return WF_OK;
-    enc::point_mask_kernel<<<B, 256, 0, as_stream(stream)>>>(x, N, D, mask, valid);
+    const int slab = N < (1 << 24) ? enc::PM_SLAB : N;
+    WF_CUDA(cudaMemsetAsync(valid, 0, (size_t)B * sizeof(float), as_stream(stream)));
+    if (N > 0) {
+        enc::point_mask_kernel<<<dim3(cdiv(N, slab), B), 256, 0, as_stream(stream)>>>(x, N, D, slab, mask, valid);
+        WF_LAUNCH_CHECK();
+    }
+    enc::clamp_valid_kernel<<<cdiv(B, 256), 256, 0, as_stream(stream)>>>(valid, B);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

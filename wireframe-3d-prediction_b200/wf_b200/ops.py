@@ -362,7 +362,7 @@ def point_mask(x: torch.Tensor):
     mask = torch.empty(B, N, device=x.device, dtype=torch.uint8)
     valid = torch.empty(B, device=x.device, dtype=torch.float32)
     call("wf_point_mask", _p(x), B, N, D, _p(mask), _p(valid), _s())
-    _count()
+    _count(2)
     return mask, valid
 
 
