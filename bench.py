@@ -359,7 +359,7 @@ def main_gpu(args):
         reducer.finish()
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
         opt.step()
-        return loss.item() if want_loss else None
+        return loss if want_loss else None          # the caller reads it back (train.py:143 `.item()`)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
@@ -405,11 +405,14 @@ def main_gpu(args):
             e0.record()
             if e2e:
                 cur = nxt if nxt is not None else h2d(i % 2)
-                nxt = h2d((i + 1) % 2) if i + 1 < n else None
                 xin, tg, ev = cur
                 torch.cuda.current_stream().wait_event(ev)
-                step(xin, tg, True)                                         # D2H: the loss scalar
+                loss_t = step(xin, tg, True)
                 stage_free[i % 2] = torch.cuda.Event(); stage_free[i % 2].record()
+                # the next batch's copies are enqueued while the device works on this step (a prefetching loader's order), then
+                # the loss scalar is read back (D2H, waits for the whole step)
+                nxt = h2d((i + 1) % 2) if i + 1 < n else None
+                loss_t.item()
             else:
                 step(x, tgt, False)
             e1.record()
@@ -426,7 +429,8 @@ def main_gpu(args):
     # so multi-GPU runs settle for 20 further untimed steps; the JSON line reports the warm-up actually done.
     # Every run also settles into the sustained power state first: inside a cold 20-step region the step time drifted by ~10 %
     # (r01: 22.4 -> 24.8 ms) as the package reached its power cap, so a short region flattered the steady state.
-    n_warm = max(args.warmup, 3) + (30 if world > 1 else 20)
+    # (WF_BENCH_SETTLE overrides the settling steps: the ncu launch-list pass, whose per-launch times are cold anyway, uses 0)
+    n_warm = max(args.warmup, 3) + int(os.environ.get("WF_BENCH_SETTLE", "30" if world > 1 else "20"))
     for _ in range(n_warm):
         step(x, tgt, False)
     barrier()
@@ -458,6 +462,29 @@ def main_gpu(args):
     barrier()
     ms_e2e = timed(args.steps, e2e=True)
     barrier()
+    # ---- supplementary region (not part of `value`): the same steps with the LayerNorm side jobs switched off, so that the GEMM
+    #      launches do nothing but the GEMM -- the kernel's own tensor roofline, measured live in this process
+    pure = None
+    if ops.SIDE_JOBS and os.environ.get("WF_BENCH_NO_PURE") != "1":
+        ops.SIDE_JOBS = False
+        try:
+            timed(2, e2e=False)
+            step_ms[False] = step_ms[False][:-2]
+            ops.GEMM_PROFILE = []
+            barrier()
+            n_pure = max(2, min(args.steps, 5))
+            ms_pure = timed(n_pure, e2e=False)
+            step_ms[False] = step_ms[False][:-n_pure]
+            barrier()
+            prof_pure, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+            g_ms = sum(r[0].elapsed_time(r[1]) for r in prof_pure)
+            g_fl = sum(r[2] for r in prof_pure)
+            pure = {"steps": n_pure, "ms_per_step": ms_pure / n_pure, "gemm_ms_per_step": g_ms / n_pure,
+                    "launches_per_step": len(prof_pure) // n_pure,
+                    "achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else None}
+        finally:
+            ops.SIDE_JOBS = True
+            ops.GEMM_PROFILE = None
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -495,6 +522,10 @@ def main_gpu(args):
                          "traffic": traffic_from_profile(),
                          "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / ms if ms else None,
                          "flop_per_launch_avg": gemm_flop / max(1, len(prof)),
+                         "without_side_jobs": None if pure is None else dict(
+                             pure, frac=(pure["achieved"] / sustained if pure["achieved"] and sustained else None),
+                             what="supplementary steps after the timed regions with WF_B200_SIDE=0 semantics: the launches run "
+                                  "the GEMM only, the LayerNorm passes are stand-alone kernels"),
                          "side_jobs": {"hbm_bytes_per_step": side_bytes / max(1, args.steps), "hbm_peak_gbs": hbm_peak,
                                        "gemm_at_peak_then_passes_at_peak_ms_per_step": serial_ms / max(1, args.steps),
                                        "frac_of_serial_peaks": serial_ms / gemm_ms if gemm_ms > 0 else None},

@@ -522,6 +522,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         *reinterpret_cast<float4*>(stg + stg_v4(lane, j >> 2)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     __syncwarp();
                     const int col = col0 + lane;
+                    if (pool_rb >= 32 && pool_rows == 32) {
+                        // ---- all 32 rows exist and belong to one cloud (the usual tile): fully unrolled walk, two independent
+                        // chains (rows 0..15 / 16..31) per kind, merged with a strict comparison (ties keep the earlier row).
+                        // The generic loop below costs ~18 instructions per row (loop, swizzle arithmetic, "first row" tests) in
+                        // one dependent chain; at K = 1024 that made the epilogue longer than the tile's MMAs (tensor pipe 60 %).
+                        const float* sp = stg + (lane & 3);
+                        const int c4 = lane >> 2;
+                        float mu0 = sp[(0 * 8 + (c4 ^ 0)) * 4], mu1 = sp[(16 * 8 + (c4 ^ 0)) * 4];
+                        int au0 = 0, au1 = 16;
+                        float mm0 = 0.f, mm1 = 0.f; int am0 = -1, am1 = -1;
+                        if (pool_mbits & 1u) { mm0 = mu0; am0 = 0; }
+                        if ((pool_mbits >> 16) & 1u) { mm1 = mu1; am1 = 16; }
+#pragma unroll
+                        for (int r = 1; r < 16; ++r) {
+                            const float t0 = sp[(r * 8 + (c4 ^ (r & 7))) * 4], t1 = sp[((r + 16) * 8 + (c4 ^ (r & 7))) * 4];
+                            if (t0 > mu0) { mu0 = t0; au0 = r; }
+                            if (t1 > mu1) { mu1 = t1; au1 = r + 16; }
+                            if (((pool_mbits >> r) & 1u) && (am0 < 0 || t0 > mm0)) { mm0 = t0; am0 = r; }
+                            if (((pool_mbits >> (r + 16)) & 1u) && (am1 < 0 || t1 > mm1)) { mm1 = t1; am1 = r + 16; }
+                        }
+                        if (mu1 > mu0) { mu0 = mu1; au0 = au1; }
+                        if (am1 >= 0 && (am0 < 0 || mm1 > mm0)) { mm0 = mm1; am0 = am1; }
+                        if (col < p.N) {
+                            const int base = p.pool_idx0 + p.pool_row0 + row0 - pool_b0 * p.pool_n;
+                            const size_t o = (size_t)pool_b0 * p.N + col;
+                            pool_push(p.pool_max_u + o, mu0, (uint32_t)(base + au0));
+                            if (am0 >= 0) pool_push(p.pool_max_m + o, mm0, (uint32_t)(base + am0));
+                        }
+                    } else
 #pragma unroll 1
                     for (int seg = 0; seg < 2; ++seg) {
                         const int r_lo = seg == 0 ? 0 : pool_rb;

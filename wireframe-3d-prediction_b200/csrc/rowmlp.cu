@@ -151,28 +151,29 @@ linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[p][e] = 0.f;
 
-    // a chunk [kc, kc + 64) of this rank's range is fetched into registers (16-byte loads, in flight under the previous
-    // chunk's MMAs), then rounded to TF32 and stored; rows / columns outside the operands arrive as zeros
-    float4 xr[4], wr[4];
-    auto fetch = [&](int kc) {
+    // a chunk [kc, kc + 64) of this rank's range is fetched into registers (16-byte loads) TWO chunks ahead of its use -- a
+    // chunk's MMAs (~400 clk per warp) do not cover a global-load latency, two do --, rounded to TF32 and stored one chunk
+    // ahead; rows / columns outside the operands arrive as zeros
+    struct Regs { float4 x[4], w[4]; };
+    auto fetch = [&](Regs& rg, int kc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int id = t + i * 256, r = id >> 4, c4 = (id & 15) * 4;
-            xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < M && kc + c4 < ke) xr[i] = *reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * ldx + kc + c4);
-            wr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!TRANS) { if (n0 + r < N && kc + c4 < ke) wr[i] = *reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * ldw + kc + c4); }
-            else        { if (kc + r < ke && n0 + c4 < N) wr[i] = *reinterpret_cast<const float4*>(W + (size_t)(kc + r) * ldw + n0 + c4); }
+            rg.x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < M && kc + c4 < ke) rg.x[i] = *reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * ldx + kc + c4);
+            rg.w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!TRANS) { if (n0 + r < N && kc + c4 < ke) rg.w[i] = *reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * ldw + kc + c4); }
+            else        { if (kc + r < ke && n0 + c4 < N) rg.w[i] = *reinterpret_cast<const float4*>(W + (size_t)(kc + r) * ldw + n0 + c4); }
         }
     };
-    auto store = [&](int buf) {
+    auto store = [&](const Regs& rg, int buf) {
         float* xs = Xs + buf * 64 * LN_S;
         float* ws = Ws + buf * LN_WBUF;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int id = t + i * 256, r = id >> 4, c4 = (id & 15) * 4;
-            *reinterpret_cast<float4*>(xs + r * LN_S + c4) = tf32_rn4(xr[i]);
-            const float4 v = tf32_rn4(wr[i]);
+            *reinterpret_cast<float4*>(xs + r * LN_S + c4) = tf32_rn4(rg.x[i]);
+            const float4 v = tf32_rn4(rg.w[i]);
             if (!TRANS) *reinterpret_cast<float4*>(ws + r * LN_S + c4) = v;
             else {                                                     // [k][n], stride 66: 8-byte stores, conflict-free scalar fragment loads
                 *reinterpret_cast<float2*>(ws + r * LN_ST + c4) = make_float2(v.x, v.y);
@@ -180,13 +181,7 @@ linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
             }
         }
     };
-
-    int buf = 0;
-    if (kb < ke) { fetch(kb); store(0); }
-    __syncthreads();
-    for (int kc = kb; kc < ke; kc += LN_KC) {
-        const bool more = kc + LN_KC < ke;
-        if (more) fetch(kc + LN_KC);
+    auto mma_chunk = [&](int buf) {
         const float* xs = Xs + buf * 64 * LN_S + (mt * 16 + gid) * LN_S + 4 * tig;
         const float* wsb = Ws + buf * LN_WBUF;
 #pragma unroll
@@ -206,9 +201,27 @@ linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                 mma_tf32(acc[p], fu(xa.z), fu(xb.z), fu(xa.w), fu(xb.w), fu(wv.z), fu(wv.w));
             }
         }
-        if (more) store(buf ^ 1);
+    };
+
+    // chunk i lives in shared buffer i & 1 and came through register set i & 1
+    Regs r0, r1;
+    const int nch = kb < ke ? (ke - kb + LN_KC - 1) / LN_KC : 0;
+    if (nch > 0) fetch(r0, kb);
+    if (nch > 1) fetch(r1, kb + LN_KC);
+    if (nch > 0) store(r0, 0);
+    __syncthreads();
+    for (int i = 0; i < nch; i += 2) {
+        // even chunk i (buffer 0): set 0 is free again -> chunk i + 2; then chunk i + 1 (set 1) goes to buffer 1
+        if (i + 2 < nch) fetch(r0, kb + (i + 2) * LN_KC);
+        mma_chunk(0);
+        if (i + 1 < nch) store(r1, 1);
         __syncthreads();
-        buf ^= 1;
+        if (i + 1 >= nch) break;
+        // odd chunk i + 1 (buffer 1): set 1 is free -> chunk i + 3; chunk i + 2 (set 0) goes to buffer 0
+        if (i + 3 < nch) fetch(r1, kb + (i + 3) * LN_KC);
+        mma_chunk(1);
+        if (i + 2 < nch) store(r0, 0);
+        __syncthreads();
     }
     // ---- partial tile -> own shared memory: c0 (row g, col 2t), c1 (row g, col 2t+1), c2 / c3 rows g + 8
 #pragma unroll
