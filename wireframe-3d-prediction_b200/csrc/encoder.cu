@@ -248,8 +248,9 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f3
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
-struct Smem {
-    u64 xs2[PB][D];          // staged points, every coordinate duplicated into both halves (operand of the f32x2 ops)
+struct __align__(16) Smem {
+    u64 xs2[PB][D];          // staged points, every coordinate duplicated into both halves (operand of the f32x2 ops); read as
+                             // 16-byte pairs of coordinates (half the shared-memory instructions of 8-byte reads)
     u64 rs2[PB];             // (rstd, rstd) per staged point
     float red[NT / 32][48];  // block reductions of the prologue
     float R[48];             // packed upper-triangular factor: R[i][j], j >= i, row-major
@@ -454,7 +455,10 @@ bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float
                 decode(cur[i], d0, d1);
                 u64 z = b2;
 #pragma unroll
-                for (int k = 0; k < D; ++k) z = fma2(s.xs2[p][k], w2[k], z);       // p < PB always (staging buffer is PB long)
+                for (int k = 0; k < D; k += 2) {                                    // p < PB always (staging buffer is PB long)
+                    const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&s.xs2[p][k]);
+                    z = fma2(xv.x, w2[k], z); z = fma2(xv.y, w2[k + 1], z);
+                }
                 xh[i] = mul2(z, s.rs2[p]);
                 float y0, y1;
                 up2(fma2(xh[i], g2, be2), y0, y1);
@@ -490,7 +494,10 @@ bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float
                     ag = fma2(gy[i], xh[i], ag);
                     abe = add2(abe, gy[i]);
 #pragma unroll
-                    for (int k = 0; k < D; ++k) aW[k] = fma2(dz, s.xs2[p][k], aW[k]);
+                    for (int k = 0; k < D; k += 2) {
+                        const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&s.xs2[p][k]);
+                        aW[k] = fma2(dz, xv.x, aW[k]); aW[k + 1] = fma2(dz, xv.y, aW[k + 1]);
+                    }
                 }
             }
         }

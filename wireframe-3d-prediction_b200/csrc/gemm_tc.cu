@@ -430,6 +430,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int own_prev = -1;                                       // own-output LayerNorm: unit whose completion is still to be signalled
         Sched sched(p, m_units, w_first, w_step);
         int n_blk, mu, kb0, kb1;
+        // pool mode: the validity byte of this thread's row is fetched ONE TILE AHEAD (a second scheduler walks one item in front):
+        // read at the top of its own tile, the load's latency was exposed once per tile -- 11 % of the pooling launch's stall
+        // samples (profiles/r02_pool_source_top.txt)
+        Sched ahead(p, m_units, w_first, w_step);
+        auto mask_of = [&](int mu_) -> uint32_t {
+            const int r_ = (CL ? 2 * mu_ + crank : mu_) * BM + q * 32 + lane;
+            return (r_ < p.M && (p.pool_mask == nullptr || p.pool_mask[r_] != 0)) ? 1u : 0u;
+        };
+        uint32_t mk_next = 0;
+        bool has_next = false;
+        if (p.pool_n > 0) {
+            int an, amu, ak0, ak1;
+            if (ahead.next(an, amu, ak0, ak1)) mk_next = mask_of(amu);          // the first item's own byte
+            has_next = true;
+        }
         while (sched.next(n_blk, mu, kb0, kb1)) {
             const int m_blk = CL ? 2 * mu + crank : mu;
             const int row0 = m_blk * BM + q * 32;
@@ -438,7 +453,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // pool mode: which of this warp's 32 rows exist / are valid points, and where the next cloud starts
             uint32_t pool_mbits = 0; int pool_rows = 0, pool_b0 = 0, pool_rb = 32;
             if (p.pool_n > 0) {
-                const bool mk = row_ok && (p.pool_mask == nullptr || p.pool_mask[row] != 0);
+                const bool mk = mk_next != 0;
+                if (has_next) {
+                    int an, amu, ak0, ak1;
+                    has_next = ahead.next(an, amu, ak0, ak1);
+                    if (has_next) mk_next = mask_of(amu);
+                }
                 pool_mbits = __ballot_sync(0xffffffffu, mk);
                 pool_rows = min(32, p.M - row0);
                 pool_b0 = (p.pool_row0 + row0) / p.pool_n;
@@ -532,19 +552,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         float mu0 = sp[(0 * 8 + (c4 ^ 0)) * 4], mu1 = sp[(16 * 8 + (c4 ^ 0)) * 4];
                         int au0 = 0, au1 = 16;
                         float mm0 = 0.f, mm1 = 0.f; int am0 = -1, am1 = -1;
-                        if (pool_mbits & 1u) { mm0 = mu0; am0 = 0; }
-                        if ((pool_mbits >> 16) & 1u) { mm1 = mu1; am1 = 16; }
+                        if (pool_mbits == 0xFFFFFFFFu) {
+                            // every row is a valid point (all tiles of a cloud but its zero-padded tail): the masked maximum IS the
+                            // unmasked one -- one chain pair instead of two (4 instead of 10 instructions per row)
 #pragma unroll
-                        for (int r = 1; r < 16; ++r) {
-                            const float t0 = sp[(r * 8 + (c4 ^ (r & 7))) * 4], t1 = sp[((r + 16) * 8 + (c4 ^ (r & 7))) * 4];
-                            if (t0 > mu0) { mu0 = t0; au0 = r; }
-                            if (t1 > mu1) { mu1 = t1; au1 = r + 16; }
-                            if (((pool_mbits >> r) & 1u) && (am0 < 0 || t0 > mm0)) { mm0 = t0; am0 = r; }
-                            if (((pool_mbits >> (r + 16)) & 1u) && (am1 < 0 || t1 > mm1)) { mm1 = t1; am1 = r + 16; }
+                            for (int r = 1; r < 16; ++r) {
+                                const float t0 = sp[(r * 8 + (c4 ^ (r & 7))) * 4], t1 = sp[((r + 16) * 8 + (c4 ^ (r & 7))) * 4];
+                                if (t0 > mu0) { mu0 = t0; au0 = r; }
+                                if (t1 > mu1) { mu1 = t1; au1 = r + 16; }
+                            }
+                            if (mu1 > mu0) { mu0 = mu1; au0 = au1; }
+                            mm0 = mu0; am0 = au0;
+                        } else {
+                            if (pool_mbits & 1u) { mm0 = mu0; am0 = 0; }
+                            if ((pool_mbits >> 16) & 1u) { mm1 = mu1; am1 = 16; }
+#pragma unroll
+                            for (int r = 1; r < 16; ++r) {
+                                const float t0 = sp[(r * 8 + (c4 ^ (r & 7))) * 4], t1 = sp[((r + 16) * 8 + (c4 ^ (r & 7))) * 4];
+                                if (t0 > mu0) { mu0 = t0; au0 = r; }
+                                if (t1 > mu1) { mu1 = t1; au1 = r + 16; }
+                                if (((pool_mbits >> r) & 1u) && (am0 < 0 || t0 > mm0)) { mm0 = t0; am0 = r; }
+                                if (((pool_mbits >> (r + 16)) & 1u) && (am1 < 0 || t1 > mm1)) { mm1 = t1; am1 = r + 16; }
+                            }
+                            if (mu1 > mu0) { mu0 = mu1; au0 = au1; }
+                            if (am1 >= 0 && (am0 < 0 || mm1 > mm0)) { mm0 = mm1; am0 = am1; }
                         }
-                        if (mu1 > mu0) { mu0 = mu1; au0 = au1; }
-                        if (am1 >= 0 && (am0 < 0 || mm1 > mm0)) { mm0 = mm1; am0 = am1; }
-                        if (col < p.N) {
+                        if (col < p.N && p.pool_max_u != nullptr) {        // (nullptr: WF_B200_POOL_NOPUSH diagnosis, see the launcher)
                             const int base = p.pool_idx0 + p.pool_row0 + row0 - pool_b0 * p.pool_n;
                             const size_t o = (size_t)pool_b0 * p.N + col;
                             pool_push(p.pool_max_u + o, mu0, (uint32_t)(base + au0));
@@ -563,7 +596,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if (au < 0 || t > mu) { mu = t; au = r; }
                             if (((pool_mbits >> r) & 1u) && (am < 0 || t > mm)) { mm = t; am = r; }
                         }
-                        if (col < p.N) {
+                        if (col < p.N && p.pool_max_u != nullptr) {
                             const int b = pool_b0 + seg;
                             const int base = p.pool_idx0 + p.pool_row0 + row0 - b * p.pool_n;            // row index inside the cloud of local row 0
                             const size_t o = (size_t)b * p.N + col;
@@ -880,6 +913,9 @@ static int gemm_tc(int esz, const void* A, int lda, int a_kmajor, const void* B,
     }
     p.pool_n = 0; p.pool_row0 = 0; p.pool_idx0 = 0; p.pool_mask = nullptr; p.pool_max_u = nullptr; p.pool_max_m = nullptr;
     if (pool != nullptr) { p.pool_n = pool->n; p.pool_row0 = pool->row0; p.pool_idx0 = pool->idx0; p.pool_mask = pool->mask; p.pool_max_u = pool->max_u; p.pool_max_m = pool->max_m; }
+    // diagnosis only (results are then wrong): WF_B200_POOL_NOPUSH=1 drops the RED.MAX.64 pushes of whole-cloud tiles, to separate
+    // the cost of the column walk from the cost of the atomics
+    { const char* e = getenv("WF_B200_POOL_NOPUSH"); if (pool != nullptr && e && e[0] == '1') p.pool_max_u = nullptr; }
     // bf16 tiles that are simply stored leave through TMA (WF_B200_GEMM_TMA_STORE=0 keeps the per-thread stores)
     static const bool tma_store_env = [] { const char* e = getenv("WF_B200_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
     p.tma_store = (tma_store_env && out_dtype == WF_BF16 && !p.accumulate && pool == nullptr && p.split_stride == 0) ? 1 : 0;
