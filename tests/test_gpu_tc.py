@@ -332,11 +332,14 @@ def test_heads_tf32_dispatch(ops):
 # ----------------------------------------------------------------------------------------------
 # fused pooling: max pools in the GEMM epilogue, mean pools through the affine map, analytic backward
 # ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("masking", ["random", "all_valid", "padded_tail"])
 @pytest.mark.parametrize("B,N,K,C", [(3, 300, 256, 512), (2, 128, 64, 96), (5, 1000, 1024, 512), (1, 4099, 128, 200)])
-def test_gemm_bf16_pool_epilogue_bit_exact(ops, B, N, K, C):
+def test_gemm_bf16_pool_epilogue_bit_exact(ops, B, N, K, C, masking):
     """wf_gemm_bf16_pool: max and FIRST argmax per (cloud, channel), all rows and valid rows, must be bit-identical to
     reducing the stored fp32 output of wf_gemm_bf16 on the same operands (tile rows straddle cloud boundaries here:
-    N is not a multiple of 128/32).  Also in row chunks (row_offset) as the inference path calls it."""
+    N is not a multiple of 128/32).  Also in row chunks (row_offset) as the inference path calls it.  Masking: random
+    (the two-kind walk), all points valid and a zero-padded tail per cloud (the one-chain paths of fully valid / fully
+    invalid 32-row groups)."""
     torch.manual_seed(B * 1000 + N)
     M = B * N
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
@@ -344,10 +347,16 @@ def test_gemm_bf16_pool_epilogue_bit_exact(ops, B, N, K, C):
     # force ties: duplicate rows (same value in every channel) so that "first index" is exercised
     A[N // 2] = A[3]; A[N - 1] = A[3]
     bias = torch.randn(C, device="cuda")
-    mask = (torch.rand(B, N, device="cuda") > 0.3)
-    mask[:, 3] = False
-    if B > 1:
-        mask[1] = False                                   # a cloud without valid points
+    if masking == "random":
+        mask = (torch.rand(B, N, device="cuda") > 0.3)
+        mask[:, 3] = False
+        if B > 1:
+            mask[1] = False                               # a cloud without valid points
+    elif masking == "all_valid":
+        mask = torch.ones(B, N, device="cuda", dtype=torch.bool)
+    else:
+        mask = torch.ones(B, N, device="cuda", dtype=torch.bool)
+        mask[:, N - max(1, (2 * N) // 5):] = False        # the last 40 % of every cloud is padding
     mask_u8 = mask.to(torch.uint8).contiguous()
     pf = torch.empty(M, C, device="cuda")
     ops.gemm_bf16(A, W, M=M, N=C, K=K, bias=bias, out=pf)

@@ -552,9 +552,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         float mu0 = sp[(0 * 8 + (c4 ^ 0)) * 4], mu1 = sp[(16 * 8 + (c4 ^ 0)) * 4];
                         int au0 = 0, au1 = 16;
                         float mm0 = 0.f, mm1 = 0.f; int am0 = -1, am1 = -1;
-                        if (pool_mbits == 0xFFFFFFFFu) {
+                        if (pool_mbits == 0xFFFFFFFFu || pool_mbits == 0u) {
                             // every row is a valid point (all tiles of a cloud but its zero-padded tail): the masked maximum IS the
-                            // unmasked one -- one chain pair instead of two (4 instead of 10 instructions per row)
+                            // unmasked one -- one chain pair instead of two (4 instead of 10 instructions per row); no row valid
+                            // (inside the padded tail): there is no masked maximum
 #pragma unroll
                             for (int r = 1; r < 16; ++r) {
                                 const float t0 = sp[(r * 8 + (c4 ^ (r & 7))) * 4], t1 = sp[((r + 16) * 8 + (c4 ^ (r & 7))) * 4];
@@ -562,7 +563,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 if (t1 > mu1) { mu1 = t1; au1 = r + 16; }
                             }
                             if (mu1 > mu0) { mu0 = mu1; au0 = au1; }
-                            mm0 = mu0; am0 = au0;
+                            if (pool_mbits != 0u) { mm0 = mu0; am0 = au0; }
                         } else {
                             if (pool_mbits & 1u) { mm0 = mu0; am0 = 0; }
                             if ((pool_mbits >> 16) & 1u) { mm1 = mu1; am1 = 16; }
