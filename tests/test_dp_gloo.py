@@ -123,6 +123,86 @@ def test_sharded_gradients_equal_full_batch():
     assert q.get(timeout=10) is True, "ranks disagree after all-reduce"
 
 
+def _early_worker(rank, world, port, out):
+    """The per-layer hand-off (ops.GRAD_READY_HOOK, what EncoderPointMLP_TC.backward calls for every finished layer): gradients
+    reduced INSIDE a Function's backward must arrive once (not again when their bucket fires), only between zero() and
+    finish(), and autograd must adopt the handed-off tensors as .grad."""
+    sys.path.insert(0, os.path.join(ROOT, "wireframe-3d-prediction_b200")); sys.path.insert(0, ROOT)
+    from wf_b200 import ops
+    from wf_b200.parallel import GradAllReduce
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    class EarlyLinear(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, W, b):
+            ctx.save_for_backward(x, W)
+            return x @ W.t() + b
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, W = ctx.saved_tensors
+            dW, db, dx = dy.t() @ x, dy.sum(0), dy @ W
+            hook = ops.GRAD_READY_HOOK
+            if hook is not None:
+                calls.append(1)
+                hook([dW, db])                              # final here: reduced while the rest of the backward still runs
+            return dx, dW, db
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(6, 16); self.b = torch.nn.Linear(16, 16); self.c = torch.nn.Linear(16, 3)
+
+        def forward(self, x):
+            h = torch.relu(self.a(x))
+            h = torch.relu(EarlyLinear.apply(h, self.b.weight, self.b.bias))
+            return self.c(h)
+
+    torch.manual_seed(0)
+    net = Net()
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(8, 6, generator=g); Y = torch.randn(8, 3, generator=g)
+    sl = slice(rank * 4, rank * 4 + 4)
+    red = GradAllReduce(net, bucket_bytes=128)
+    ok = True
+    for step in range(3):                                   # step 0 builds the buckets (the hand-off is inactive until then)
+        red.zero()
+        ((net(X[sl]) - Y[sl]) ** 2).sum().backward()
+        red.finish()
+        grads = {k: p.grad.clone() for k, p in net.named_parameters()}
+    ok &= len(calls) == 3
+    torch.manual_seed(0)
+    ref = Net()
+    ((ref(X) - Y) ** 2).sum().backward()
+    for k, p in ref.named_parameters():
+        ok &= bool(torch.allclose(grads[k], p.grad, rtol=1e-5, atol=1e-6))
+    # outside zero()/finish() the hook must not start a collective (another model's backward may run between steps)
+    n_before = len(red._handles)
+    probe = torch.ones(4) * (rank + 1)
+    ops.GRAD_READY_HOOK([probe])
+    ok &= len(red._handles) == n_before and bool(torch.equal(probe, torch.ones(4) * (rank + 1)))
+    red.remove()
+    ok &= ops.GRAD_READY_HOOK is None
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_early_gradient_handoff_is_reduced_exactly_once():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_early_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
+
+
 def test_shard_loss_weights_sum_rules():
     sys.path.insert(0, os.path.join(ROOT, "wireframe-3d-prediction_b200"))
     from wf_b200.parallel import shard_loss_weights

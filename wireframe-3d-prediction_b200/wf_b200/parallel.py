@@ -191,6 +191,14 @@ class GradAllReduce:
         if self.world == 1:
             return
         self._check_registered()
+        if self._early_ptrs:
+            # the early hand-off reduces the tensors a Function is about to return; that is only right if autograd then ADOPTS
+            # them as .grad (no copy).  A copied gradient would have been cloned while its source was being reduced.
+            held = {q.grad.data_ptr() for q in self.module.parameters() if q.grad is not None}
+            if not self._early_ptrs <= held:
+                raise RuntimeError("GradAllReduce: a gradient handed off inside backward was copied by autograd instead of being "
+                                   "adopted as .grad; the early all-reduce cannot be used with this graph (set "
+                                   "ops.GRAD_READY_HOOK = None)")
         if not self._built:
             self._build()
             self._launch([p.grad for b in self.buckets for p in b["params"]])
