@@ -74,3 +74,20 @@ def test_items_without_a_window_run_stand_alone_and_random_plans_are_valid():
             items.append(ss.Item(k, r0, r0 + rnd.randint(1, 400000), rnd.choice([4096, 8192, 6144, 12288]), a, d))
         side, pre = ss.plan(durs, items, rnd.choice([5e11, 2e12, 1e13]))
         _check(durs, items, side, pre)
+
+
+def test_plan_cached_equals_plan_and_is_not_disturbed_by_reuse():
+    """plan_cached memoises the plan on (durations, item windows, bandwidth): same result as plan(), also on the second request
+    (Item.done of the caller's objects is not part of the key and is left alone)."""
+    from wf_b200 import sidesched as ss
+    durs = [1.0e-3, 0.5e-3, 2.0e-3, 1.0e-3, 1.5e-3, 0.7e-3, 1.1e-3, 0.9e-3]
+    mk = lambda: [ss.Item((li, c), c * 320000, (c + 1) * 320000, 4096.0 * (1 + li % 2), li * 2 + c, (li + 1) * 2 + c)
+                  for li in range(3) for c in range(2)]
+    ref_side, ref_pre = ss.plan(durs, mk(), 2.0e12)
+    for _ in range(2):
+        items = mk()
+        side, pre = ss.plan_cached(durs, items, 2.0e12)
+        assert [list(x) for x in side] == ref_side and {k: list(v) for k, v in pre.items()} == ref_pre
+        assert all(it.done == 0 for it in items)
+    other, _ = ss.plan_cached(durs, mk(), 1.0e12)              # another bandwidth is another plan
+    assert [list(x) for x in other] != ref_side

@@ -590,7 +590,7 @@ def _enc_mlp_forward(h1, layers, wbs, w5b, b5, *, zs, hs, means, rstds, mask, po
     durs = [2.0 * (chunks[c][1] - chunks[c][0]) * dims[li][0] * dims[li][1] / _GEMM_RATE for (li, c) in launches]
     items = [ss.Item((li, c), chunks[c][0], chunks[c][1], dims[li][0] * 4.0, idx[(li, c)], idx[(li + 1, c)])
              for li in range(nl) for c in range(nc)]
-    side, pre = ss.plan(durs, items, SIDE_BW)
+    side, pre = ss.plan_cached(durs, items, SIDE_BW)
     colsum = (mask, part, pool_n, row_base)
 
     def seg_of(key, r0, r1):
@@ -644,7 +644,7 @@ def _enc_mlp_backward(dh_top, hs, zs, means, rstds, layers, sms):
             if not _use_side(m):
                 avail = idx[("dX", li, c)] - 1               # no window: a stand-alone pass right before its consumer
             items.append(ss.Item((li, c), chunks[c][0], chunks[c][1], layers[li][0].shape[0] * 6.0, avail, idx[("dX", li, c)]))
-    side, pre = ss.plan(durs, items, SIDE_BW)
+    side, pre = ss.plan_cached(durs, items, SIDE_BW)
     dhs = {nl - 1: dh_top}
     dzs, grads, dWs, wts = {}, {}, {}, {}
     for li in range(nl):
