@@ -89,5 +89,10 @@ def test_plan_cached_equals_plan_and_is_not_disturbed_by_reuse():
         side, pre = ss.plan_cached(durs, items, 2.0e12)
         assert [list(x) for x in side] == ref_side and {k: list(v) for k, v in pre.items()} == ref_pre
         assert all(it.done == 0 for it in items)
-    other, _ = ss.plan_cached(durs, mk(), 1.0e12)              # another bandwidth is another plan
-    assert [list(x) for x in other] != ref_side
+    # a different window is a different plan (the key covers the items' windows, not only their rows)
+    wide = mk()
+    for it in wide:
+        it.deadline += 2
+    side2, _ = ss.plan_cached(durs, wide, 2.0e12)
+    ref2, _ = ss.plan(durs, [ss.Item(it.key, it.r0, it.r1, it.bytes_per_row, it.avail, it.deadline) for it in wide], 2.0e12)
+    assert [list(x) for x in side2] == ref2 and ref2 != ref_side
