@@ -160,7 +160,7 @@ def _tc_operand_ok(t: torch.Tensor) -> bool:
             and t.data_ptr() % 16 == 0)
 
 
-def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0, bias=None, tc=True):
+def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0, bias=None, tc=True, colsum_out=None):
     """C = alpha * op(A) op(B) + beta * C (+ bias), fp32 storage.
     Production precision ('bf16' mode): large, 16-byte-aligned products run on the tensor cores as TF32
     (wf_gemm_tf32, tcgen05 kind::tf32, fp32 accumulate); everything else, and the whole 'fp32' parity mode,
@@ -178,7 +178,11 @@ def gemm_f32(A, B, *, transA=False, transB=False, out=None, beta=0.0, alpha=1.0,
         if rows <= _ROWMLP_MAX_ROWS:
             if transA and not transB and bias is None and M % 4 == 0 and N % 4 == 0 and M * N >= _ROWMLP_MIN_WEIGHTS:
                 out = torch.empty(M, N, device=A.device, dtype=torch.float32)        # dW[Nr, Kc] = A^T B, reduction over the rows
-                call("wf_rowmlp_dw", _p(A), A.stride(0), _p(B), B.stride(0), rows, M, N, _p(out), out.stride(0), None, _s())
+                # colsum_out (a list): the bias gradient db = column sums of A comes out of the same launch
+                db = torch.empty(M, device=A.device, dtype=torch.float32) if colsum_out is not None else None
+                call("wf_rowmlp_dw", _p(A), A.stride(0), _p(B), B.stride(0), rows, M, N, _p(out), out.stride(0), _p(db), _s())
+                if colsum_out is not None:
+                    colsum_out.append(db)
                 _count()
                 return out
             if not transA and N % 4 == 0 and K % 4 == 0 and N * K >= _ROWMLP_MIN_WEIGHTS:
@@ -286,10 +290,9 @@ class LinearLNAct(torch.autograd.Function):
         d2 = _f32c(dout.reshape(-1, C))
         M = d2.shape[0]
         dgamma = dbeta = db = None
+        want_db_plain = plain and has_b and ctx.needs_input_grad[2]
         if plain:
             dz = d2
-            if has_b and ctx.needs_input_grad[2]:
-                db = colsum(dz)
         else:
             dz = torch.empty_like(d2)
             if gamma is not None:
@@ -303,7 +306,12 @@ class LinearLNAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm_f32(dz, Wc).reshape(xshape)
         if ctx.needs_input_grad[1]:
-            dW = gemm_f32(dz, x2, transA=True)
+            got = [] if want_db_plain else None
+            dW = gemm_f32(dz, x2, transA=True, colsum_out=got)
+            if got:
+                db = got[0]                                  # the row-MLP dW kernel also returned the column sums of dz
+        if want_db_plain and db is None:
+            db = colsum(dz)
         dres = dout if has_res else None
         return dx, dW, db, dgamma, dbeta, None, dres, None, None
 
