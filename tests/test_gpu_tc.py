@@ -390,12 +390,14 @@ def test_gemm_bf16_pool_epilogue_bit_exact(ops, B, N, K, C, masking):
         assert torch.equal(args[0].long(), exp_am), "masked argmax differs"
 
 
-def test_ln_colsum_and_seg_mean(ops):
+@pytest.mark.parametrize("B,N", [(3, 333), (2, 20011)])
+def test_ln_colsum_and_seg_mean(ops, B, N):
     """wf_ln_relu_bf16_fwd_colsum writes the same h as wf_ln_relu_bf16_fwd and wf_seg_mean returns the per-cloud means of
-    that h (all rows / valid rows) -- also when called in row chunks."""
+    that h (all rows / valid rows) -- also when called in row chunks.  The 20 011-point clouds have 157 row blocks each: the
+    interleaved ranges of wf_seg_mean take several blocks per thread, and the cloud boundary falls inside a block."""
     from wf_b200._lib import call
     torch.manual_seed(11)
-    B, N, C = 3, 333, 1024
+    C = 1024
     M = B * N
     z = (torch.randn(M, C, device="cuda") * 1.5).to(torch.bfloat16)
     mean = z.float().mean(1).contiguous(); rstd = (z.float().var(1, unbiased=False) + 1e-5).rsqrt().contiguous()
@@ -529,6 +531,12 @@ def test_encoder_inference_chunked_is_bit_identical(ops):
             ops.INFER_CHUNK_ROWS = old
         for a, b, n in zip(out, ref, ("max_m", "avg_m", "max_u", "mean_u", "arg_m", "arg_u")):
             assert torch.equal(a, b), f"chunk {chunk}: {n} differs"
+    # the L2-resident form: small chunks through two ping-pong buffers, LayerNorm in place (ops.encoder_pooled_infer)
+    xin, params = enc.tc_inputs(x)
+    with torch.no_grad():
+        out = ops.encoder_pooled_infer(xin, [t.detach() for t in params], l2_resident=True, chunk_rows=512)
+    for a, b, n in zip(out, ref, ("max_m", "avg_m", "max_u", "mean_u", "arg_m", "arg_u")):
+        assert torch.equal(a, b), f"L2-resident form: {n} differs"
 
 
 def test_encoder_point_sharded_matches_unsharded(ops):
