@@ -35,6 +35,20 @@ def test_library_exports_header_symbols():
     assert lib.wf_version() >= 100
 
 
+def test_every_entry_point_the_package_calls_is_bound():
+    """Every `call("wf_...")` in the product package names an entry point of the binding (a typo would otherwise only surface
+    on a GPU box), with as many arguments as its ctypes signature for the calls whose argument list is on one level."""
+    import glob
+    from wf_b200 import _lib
+    used = {}
+    for f in glob.glob(os.path.join(ROOT, "wireframe-3d-prediction_b200", "**", "*.py"), recursive=True):
+        for m in re.finditer(r'call\(\s*"(wf_[a-z0-9_]+)"', open(f).read()):
+            used.setdefault(m.group(1), []).append(os.path.relpath(f, ROOT))
+    assert len(used) >= 40
+    for name, where in used.items():
+        assert name in _lib.SIGNATURES, f"{where[0]} calls {name}, which the binding does not declare"
+
+
 def test_state_dict_keys_match_reference_inventory():
     from oracle import wireframe_oracle as wo
     from models.PointCloudToWireframe import PointCloudToWireframe
