@@ -344,11 +344,13 @@ int wf_attn_bwd(const float* d_out, const float* qkv, const float* probs, const 
  * pairs (i<j) in the reference's row-major order.  P,Q are the per-vertex halves of the layer. */
 int wf_edge_pair_fwd(const float* P, const float* Q, const float* verts, const float* wd,
                      const float* bias, const int32_t* v_off, const int64_t* e_off, int B, int T,
-                     int C, float* z1, float* dist, wf_stream_t stream);
+                     int C, int ld, float* z1, float* dist, wf_stream_t stream);
 /* dP,dQ [T,C] written; d_verts [T,3] and d_wd[C] accumulated (caller zeroes).  The bias gradient
- * is the column sum of dP (every pair contributes once to exactly one dP row): use wf_colsum. */
+ * is the column sum of dP (every pair contributes once to exactly one dP row): use wf_colsum.
+ * ld: row stride in floats of P, Q (forward) and dP, dQ (backward) -- 2C when they are the two halves of ONE
+ * stacked [T, 2C] product, so that neither the halves nor their gradients are ever copied apart. */
 int wf_edge_pair_bwd(const float* dz1, const float* dist, const float* verts, const float* wd,
-                     const int32_t* v_off, const int64_t* e_off, int B, int T, int C, float* dP,
+                     const int32_t* v_off, const int64_t* e_off, int B, int T, int C, int ld, float* dP,
                      float* dQ, float* d_verts, float* d_wd, wf_stream_t stream);
 
 /* edge_mlp.10 + sigmoid + zero-padding to (B, max_e): models/EdgePredictor.py:137-138,

@@ -234,7 +234,8 @@ def test_edge_pair_and_out(ops):
     go = torch.randn_like(padded); padded.backward(go)
     leaves = [P, Q, verts, wd, bias, Wm, w_out, b_out]
     f = [t.detach().float().requires_grad_(True) for t in leaves]
-    z = ops.EdgePairLayer.apply(f[0], f[1], f[2], f[3], f[4], rg)
+    pq = torch.cat([f[0], f[1]], dim=1)                     # the layer takes the stacked [P | Q] product
+    z = ops.EdgePairLayer.apply(pq, f[2], f[3], f[4], rg)
     assert_close(z, z_ref, 1e-5, "pair fwd")
     h = ops.linear_ln_act(z, f[5], None, None, None, 2)
     out = ops.EdgeOut.apply(h, f[6], f[7], rg)

@@ -221,7 +221,7 @@ attn_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ qkv, 
 __global__ void __launch_bounds__(256)
 edge_pair_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ verts,
                      const float* __restrict__ wd, const float* __restrict__ bias, const int* __restrict__ v_off,
-                     const long long* __restrict__ e_off, int B, int C, float* __restrict__ z1, float* __restrict__ dist) {
+                     const long long* __restrict__ e_off, int B, int C, int ld, float* __restrict__ z1, float* __restrict__ dist) {
     const int t = blockIdx.x;
     const int b = find_segment(v_off, B, t);
     const int t0 = v_off[b], c = v_off[b + 1] - t0, i = t - t0;
@@ -230,13 +230,13 @@ edge_pair_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Q, c
     const long long e0 = e_off[b] + pair_id(i, i + 1, c);
     const float vx = verts[(size_t)t * 3], vy = verts[(size_t)t * 3 + 1], vz = verts[(size_t)t * 3 + 2];
     const int C4 = C >> 2;
-    if ((C & 3) == 0 && C4 <= (int)blockDim.x && (blockDim.x % C4) == 0 &&
+    if ((C & 3) == 0 && (ld & 3) == 0 && C4 <= (int)blockDim.x && (blockDim.x % C4) == 0 &&
         ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(wd) |
           reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(z1)) & 15) == 0) {
         // a thread keeps four channels of this vertex's P row, the distance weights and the bias in registers and walks the
         // partner vertices: one float4 of Q in, one float4 of z1 out per pair (the distance is formed once per 4 channels)
         const int c4 = threadIdx.x % C4, j0 = threadIdx.x / C4, jstep = blockDim.x / C4;
-        const float4 p4 = reinterpret_cast<const float4*>(P + (size_t)t * C)[c4];
+        const float4 p4 = reinterpret_cast<const float4*>(P + (size_t)t * ld)[c4];
         const float4 w4 = reinterpret_cast<const float4*>(wd)[c4];
         const float4 b4 = reinterpret_cast<const float4*>(bias)[c4];
         for (int jj = j0; jj < nj; jj += jstep) {
@@ -244,7 +244,7 @@ edge_pair_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Q, c
             const float dx = vx - verts[(size_t)tj * 3], dy = vy - verts[(size_t)tj * 3 + 1], dz = vz - verts[(size_t)tj * 3 + 2];
             const float dd = sqrtf(dx * dx + dy * dy + dz * dz);
             if (c4 == 0) dist[e0 + jj] = dd;
-            const float4 q4 = reinterpret_cast<const float4*>(Q + (size_t)tj * C)[c4];
+            const float4 q4 = reinterpret_cast<const float4*>(Q + (size_t)tj * ld)[c4];
             // same association as the scalar form: ((P + Q) + wd * d) + bias
             float4 o;
             o.x = p4.x + q4.x + w4.x * dd + b4.x; o.y = p4.y + q4.y + w4.y * dd + b4.y;
@@ -259,7 +259,7 @@ edge_pair_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Q, c
         const float dx = vx - verts[(size_t)tj * 3], dy = vy - verts[(size_t)tj * 3 + 1], dz = vz - verts[(size_t)tj * 3 + 2];
         const float dd = sqrtf(dx * dx + dy * dy + dz * dz);
         if (ch == 0) dist[e0 + jj] = dd;
-        z1[(size_t)(e0 + jj) * C + ch] = P[(size_t)t * C + ch] + Q[(size_t)tj * C + ch] + wd[ch] * dd + bias[ch];
+        z1[(size_t)(e0 + jj) * C + ch] = P[(size_t)t * ld + ch] + Q[(size_t)tj * ld + ch] + wd[ch] * dd + bias[ch];
     }
 }
 
@@ -267,7 +267,7 @@ template <int CPL>     // channels per lane = C / 32
 __global__ void __launch_bounds__(256)
 edge_pair_bwd_kernel(const float* __restrict__ dz1, const float* __restrict__ dist, const float* __restrict__ verts,
                      const float* __restrict__ wd, const int* __restrict__ v_off, const long long* __restrict__ e_off, int B,
-                     float* __restrict__ dP, float* __restrict__ dQ, float* __restrict__ d_verts, float* __restrict__ d_wd) {
+                     int ld, float* __restrict__ dP, float* __restrict__ dQ, float* __restrict__ d_verts, float* __restrict__ d_wd) {
     constexpr int C = CPL * 32;
     __shared__ float red[8][C];
     const int t = blockIdx.x;
@@ -319,8 +319,8 @@ edge_pair_bwd_kernel(const float* __restrict__ dz1, const float* __restrict__ di
         }
         __syncthreads();
     };
-    reduce_store(accP, dP + (size_t)t * C, false);
-    reduce_store(accQ, dQ + (size_t)t * C, false);
+    reduce_store(accP, dP + (size_t)t * ld, false);
+    reduce_store(accQ, dQ + (size_t)t * ld, false);
     reduce_store(accW, d_wd, true);
 }
 
@@ -439,25 +439,27 @@ extern "C" int wf_attn_bwd(const float* d_out, const float* qkv, const float* pr
 }
 
 extern "C" int wf_edge_pair_fwd(const float* P, const float* Q, const float* verts, const float* wd, const float* bias,
-                                const int32_t* v_off, const int64_t* e_off, int B, int T, int C, float* z1, float* dist,
+                                const int32_t* v_off, const int64_t* e_off, int B, int T, int C, int ld, float* z1, float* dist,
                                 wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || T <= 0) return WF_OK;
-    edge::edge_pair_fwd_kernel<<<T, 256, 0, as_stream(stream)>>>(P, Q, verts, wd, bias, v_off, reinterpret_cast<const long long*>(e_off), B, C, z1, dist);
+    WF_CHECK_ARG(ld >= C, "wf_edge_pair_fwd: row stride %d < C = %d", ld, C);
+    edge::edge_pair_fwd_kernel<<<T, 256, 0, as_stream(stream)>>>(P, Q, verts, wd, bias, v_off, reinterpret_cast<const long long*>(e_off), B, C, ld, z1, dist);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
 
 extern "C" int wf_edge_pair_bwd(const float* dz1, const float* dist, const float* verts, const float* wd, const int32_t* v_off,
-                                const int64_t* e_off, int B, int T, int C, float* dP, float* dQ, float* d_verts, float* d_wd,
+                                const int64_t* e_off, int B, int T, int C, int ld, float* dP, float* dQ, float* d_verts, float* d_wd,
                                 wf_stream_t stream) {
     using namespace wf;
     if (B <= 0 || T <= 0) return WF_OK;
+    WF_CHECK_ARG(ld >= C, "wf_edge_pair_bwd: row stride %d < C = %d", ld, C);
     WF_CHECK_ARG(C == 128 || C == 256 || C == 512 || C == 1024, "wf_edge_pair_bwd: C=%d not built (128, 256, 512, 1024)", C);
 #define WF_PAIR_BWD(CPL_)                                                                                                     \
     case CPL_ * 32:                                                                                                           \
         edge::edge_pair_bwd_kernel<CPL_><<<T, 256, 0, as_stream(stream)>>>(                                                   \
-            dz1, dist, verts, wd, v_off, reinterpret_cast<const long long*>(e_off), B, dP, dQ, d_verts, d_wd);                \
+            dz1, dist, verts, wd, v_off, reinterpret_cast<const long long*>(e_off), B, ld, dP, dQ, d_verts, d_wd);            \
         break;
     switch (C) { WF_PAIR_BWD(4) WF_PAIR_BWD(8) WF_PAIR_BWD(16) WF_PAIR_BWD(32) }
 #undef WF_PAIR_BWD

@@ -62,13 +62,12 @@ class EdgePredictor(nn.Module):
         ka, kas = ops.dropout_keep((rg.Ptot,), p_att, p_att > 0.0, dev)
         o = ops.AttentionCore.apply(qkv, rg, ka, kas, self._dims[2])
         f = ops.linear_ln_act(o, att.out_proj.weight, att.out_proj.bias, residual=f)       # reference :114
-        W1 = em[0].weight                                                                   # (H, 2H + 7): (512, 1031)
-        # first edge layer on [f_i | f_j | v_i | v_j | dist] = P[i] + Q[j] + w*dist: both feature blocks in ONE product
-        # against the stacked, contiguous (2H, H) weight (the 2H + 7-wide rows are not 16-byte aligned for TMA)
-        Wf = torch.cat([W1[:, :H], W1[:, H:2 * H]], dim=0)
-        Wv = torch.cat([W1[:, 2 * H:2 * H + 3], W1[:, 2 * H + 3:2 * H + 6]], dim=0)
-        PQ = ops.linear_ln_act(verts, Wv, residual=ops.linear_ln_act(f, Wf))               # (T, 1024)
-        z1 = ops.EdgePairLayer.apply(PQ[:, :H], PQ[:, H:], verts, W1[:, 2 * H + 6], em[0].bias, rg)
+        # first edge layer on [f_i | f_j | v_i | v_j | dist] = P[i] + Q[j] + w*dist: both feature blocks in ONE product against the
+        # stacked, contiguous (2H, H) weight (the 2H + 7-wide rows of edge_mlp.0.weight are not 16-byte aligned for TMA); the
+        # pair kernels read P and Q as the two halves of that product
+        Wf, Wv, wd = ops.SplitPairWeight.apply(em[0].weight)                                # (H, 2H + 7): (512, 1031)
+        PQ = ops.linear_ln_act(verts, Wv, residual=ops.linear_ln_act(f, Wf))               # (T, 2H)
+        z1 = ops.EdgePairLayer.apply(PQ, verts, wd, em[0].bias, rg)
         k, ks = self._keep((rg.E, H), em[3], dev)
         e = ops.LNAct.apply(z1, em[1].weight, em[1].bias, ACT_GELU, k, ks)
         k, ks = self._keep((rg.E, H // 2), em[7], dev)

@@ -64,8 +64,8 @@ SIGNATURES = {
     "wf_scatter_prefix_add": [P, I, I, P, I, P, P],
     "wf_attn_fwd": [P, P, P, I, I, I, I, P, P, P, F, P],
     "wf_attn_bwd": [P, P, P, P, P, I, I, I, I, P, P, F, P],
-    "wf_edge_pair_fwd": [P, P, P, P, P, P, P, I, I, I, P, P, P],
-    "wf_edge_pair_bwd": [P, P, P, P, P, P, I, I, I, P, P, P, P, P],
+    "wf_edge_pair_fwd": [P, P, P, P, P, P, P, I, I, I, I, P, P, P],
+    "wf_edge_pair_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P],
     "wf_edge_out_fwd": [P, P, P, P, I, I, I, P, P],
     "wf_edge_out_bwd": [P, P, P, P, P, I, I, I, P, P, P, P],
     "wf_hausdorff_lines": [P, P, P, P, P, I, I, P, I, P, P],

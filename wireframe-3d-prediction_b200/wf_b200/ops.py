@@ -1072,17 +1072,19 @@ class AttentionCore(torch.autograd.Function):
 
 class EdgePairLayer(torch.autograd.Function):
     """z1[e=(i,j)] = P[i] + Q[j] + wd * |v_i - v_j| + b  (models/EdgePredictor.py:117-134 + edge_mlp.0
-    without the (E,1031) concat)."""
+    without the (E,1031) concat).  PQ = [P | Q] is the ONE stacked [T, 2C] product of the vertex features with both feature
+    blocks of the layer: the kernels read the halves in place (row stride 2C) and write their gradients into one [T, 2C]
+    tensor, so neither the halves nor their gradients are copied apart or added back together by autograd."""
 
     @staticmethod
-    def forward(ctx, P, Q, verts, wd, bias, rg: Ragged):
-        _need_cuda(P)
-        P, Q, verts, wd, bias = _f32c(P), _f32c(Q), _f32c(verts), _f32c(wd), _f32c(bias)
-        C = P.shape[1]
-        z1 = torch.empty(rg.E, C, device=P.device, dtype=torch.float32)
-        dist = torch.empty(rg.E, device=P.device, dtype=torch.float32)
-        call("wf_edge_pair_fwd", _p(P), _p(Q), _p(verts), _p(wd), _p(bias), _p(rg.v_off), _p(rg.e_off), rg.B, rg.T, C,
-             _p(z1), _p(dist), _s())
+    def forward(ctx, PQ, verts, wd, bias, rg: Ragged):
+        _need_cuda(PQ)
+        PQ, verts, wd, bias = _f32c(PQ), _f32c(verts), _f32c(wd), _f32c(bias)
+        C = PQ.shape[1] // 2
+        z1 = torch.empty(rg.E, C, device=PQ.device, dtype=torch.float32)
+        dist = torch.empty(rg.E, device=PQ.device, dtype=torch.float32)
+        call("wf_edge_pair_fwd", _p(PQ), c_void_p(PQ.data_ptr() + 4 * C), _p(verts), _p(wd), _p(bias), _p(rg.v_off), _p(rg.e_off),
+             rg.B, rg.T, C, 2 * C, _p(z1), _p(dist), _s())
         _count()
         ctx.save_for_backward(dist, verts, wd)
         ctx.rg = rg
@@ -1094,15 +1096,47 @@ class EdgePairLayer(torch.autograd.Function):
         rg = ctx.rg
         C = wd.shape[0]
         dz1 = _f32c(dz1)
-        dP = torch.empty(rg.T, C, device=dz1.device, dtype=torch.float32)
-        dQ = torch.empty(rg.T, C, device=dz1.device, dtype=torch.float32)
+        dPQ = torch.empty(rg.T, 2 * C, device=dz1.device, dtype=torch.float32)
         dv = zeros_f32(rg.T, 3, device=dz1.device)
         dwd = zeros_f32(C, device=dz1.device)
-        call("wf_edge_pair_bwd", _p(dz1), _p(dist), _p(verts), _p(wd), _p(rg.v_off), _p(rg.e_off), rg.B, rg.T, C, _p(dP),
-             _p(dQ), _p(dv), _p(dwd), _s())
+        call("wf_edge_pair_bwd", _p(dz1), _p(dist), _p(verts), _p(wd), _p(rg.v_off), _p(rg.e_off), rg.B, rg.T, C, 2 * C, _p(dPQ),
+             c_void_p(dPQ.data_ptr() + 4 * C), _p(dv), _p(dwd), _s())
         _count()
-        dbias = colsum(dP)
-        return dP, dQ, dv, dwd, dbias, None
+        dbias = colsum(dPQ[:, :C])                           # every pair contributes once to exactly one dP row
+        return dPQ, dv, dwd, dbias, None
+
+
+class SplitPairWeight(torch.autograd.Function):
+    """edge_mlp.0.weight [H, 2H + 7] -> (Wfq [2H, H]: the two feature blocks stacked, Wvq [2H, 3]: the two coordinate blocks
+    stacked, wd [H]: the distance column) as contiguous operands, and back: ONE assembly of the weight gradient instead of
+    autograd's slice / cat backward per use (a zero-filled [H, 2H + 7] tensor, a copy and an add for each of the five slices)."""
+
+    @staticmethod
+    def forward(ctx, W1):
+        H = W1.shape[0]
+        ctx.H = H
+        Wfq = torch.cat([W1[:, :H], W1[:, H:2 * H]], dim=0)
+        Wvq = torch.cat([W1[:, 2 * H:2 * H + 3], W1[:, 2 * H + 3:2 * H + 6]], dim=0)
+        return Wfq, Wvq, W1[:, 2 * H + 6].contiguous()
+
+    @staticmethod
+    def backward(ctx, dWfq, dWvq, dwd):
+        H = ctx.H
+        ref = next(g for g in (dWfq, dWvq, dwd) if g is not None)
+        dW1 = torch.empty(H, 2 * H + 7, device=ref.device, dtype=ref.dtype)
+        if dWfq is not None:
+            dW1[:, :H] = dWfq[:H]; dW1[:, H:2 * H] = dWfq[H:]
+        else:
+            dW1[:, :2 * H] = 0
+        if dWvq is not None:
+            dW1[:, 2 * H:2 * H + 3] = dWvq[:H]; dW1[:, 2 * H + 3:2 * H + 6] = dWvq[H:]
+        else:
+            dW1[:, 2 * H:2 * H + 6] = 0
+        if dwd is not None:
+            dW1[:, 2 * H + 6] = dwd
+        else:
+            dW1[:, 2 * H + 6] = 0
+        return dW1
 
 
 class EdgeOut(torch.autograd.Function):
